@@ -1,0 +1,193 @@
+// K1: fused camera -> ray -> trilinear fetch -> emission-absorption composite (forward + backward).
+//
+// Replaces reference models/volume_render.py:53-63 (PyTorch3D NDCGridRaysampler + VolumeSampler +
+// EmissionAbsorptionRaymarcher + README.md:26-33 depth patch).  Nothing between the channels-last
+// volume and the [N,S,S,16]+sil+depth images touches HBM.
+//
+// Work mapping: 4 lanes ("quad") per ray, lane c owns feature channels 4c..4c+3 as one float4, so
+// every corner fetch of a ray is one coalesced 64-byte read; a warp marches a 4x2 pixel patch
+// (neighbouring rays are ~0.5 voxel apart, so their corner reads share 128-byte lines in L1) and a
+// 256-thread CTA an 8x8 pixel tile.  Density corners are split over the quad (2 per lane) and
+// combined with two xor-shuffles.  Samples outside the exact ray/volume slab are skipped (they
+// contribute exactly 0 under zeros padding and multiply the transmittance by exactly 1).
+#include "common.cuh"
+
+namespace forge {
+
+constexpr int kRmThreads = 256;
+constexpr int kMaxP = 512;
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz;
+    int k0, k1;   // conservative sample range that can touch the volume
+};
+
+__device__ __forceinline__ void axis_slab(float o, float d, float lim, float& zlo, float& zhi) {
+    if (d != 0.f) {
+        const float t1 = (-lim - o) / d, t2 = (lim - o) / d;
+        zlo = fmaxf(zlo, fminf(t1, t2));
+        zhi = fminf(zhi, fmaxf(t1, t2));
+    } else if (fabsf(o) >= lim) {
+        zlo = 1.f;
+        zhi = 0.f;   // empty
+    }
+}
+
+__device__ __forceinline__ Ray make_ray(const float* __restrict__ cam, int i, int j, const float* zs, int P, int D, int H,
+                                        int W) {
+    Ray r;
+    const float u = static_cast<float>(j) + 0.5f, v = static_cast<float>(i) + 0.5f;
+    r.ox = cam[0];
+    r.oy = cam[1];
+    r.oz = cam[2];
+    r.dx = fmaf(cam[3], u, fmaf(cam[4], v, cam[5]));
+    r.dy = fmaf(cam[6], u, fmaf(cam[7], v, cam[8]));
+    r.dz = fmaf(cam[9], u, fmaf(cam[10], v, cam[11]));
+    // a sample can touch the volume only if every unnormalised coordinate lies in (-1, size):
+    // |p_axis| < 1 + 2/(size-1).  Solve for z per axis, widen by one sample on each side.
+    float zlo = -3.0e38f, zhi = 3.0e38f;
+    axis_slab(r.ox, r.dx, 1.f + 2.f / static_cast<float>(W - 1), zlo, zhi);
+    axis_slab(r.oy, r.dy, 1.f + 2.f / static_cast<float>(H - 1), zlo, zhi);
+    axis_slab(r.oz, r.dz, 1.f + 2.f / static_cast<float>(D - 1), zlo, zhi);
+    r.k0 = 0;
+    r.k1 = P;
+    if (zlo > zhi) {
+        r.k1 = 0;
+    } else if (P >= 2) {
+        const float z0 = zs[0], dzs = (zs[P - 1] - zs[0]) / static_cast<float>(P - 1);
+        if (dzs > 0.f) {
+            const float a = fminf(fmaxf((zlo - z0) / dzs, -2.f), static_cast<float>(P) + 2.f);
+            const float b = fminf(fmaxf((zhi - z0) / dzs, -2.f), static_cast<float>(P) + 2.f);
+            r.k0 = max(0, static_cast<int>(floorf(a)) - 1);
+            r.k1 = min(P, static_cast<int>(ceilf(b)) + 2);
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ Tri sample_tri(const Ray& r, float z, int D, int H, int W) {
+    // points = origins + lengths * directions, rounded like the reference's separate mul and add
+    const float px = __fadd_rn(r.ox, __fmul_rn(z, r.dx));
+    const float py = __fadd_rn(r.oy, __fmul_rn(z, r.dy));
+    const float pz = __fadd_rn(r.oz, __fmul_rn(z, r.dz));
+    return make_tri(unnormalize_ac(px, W), unnormalize_ac(py, H), unnormalize_ac(pz, D), D, H, W);
+}
+
+// density at the sample: lane c of the quad fetches corners (dz = c>>1, dy = c&1, dx = 0/1)
+__device__ __forceinline__ float quad_density(const Tri& t, const float* __restrict__ dens, int H, int W, int c) {
+    const int c0 = ((c >> 1) << 2) | ((c & 1) << 1);
+    const int zz = t.z0 + (c >> 1), yy = t.y0 + (c & 1);
+    const long long row = (static_cast<long long>(zz) * H + yy) * W + t.x0;
+    float part = 0.f;
+    if ((t.mask >> c0) & 1u) part = __ldg(dens + row) * tri_weight(t, c0);
+    if ((t.mask >> (c0 + 1)) & 1u) part = fmaf(__ldg(dens + row + 1), tri_weight(t, c0 + 1), part);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    return part;
+}
+
+__device__ __forceinline__ void tile_coords(int& i, int& j, int tiles_x) {
+    const int warp = threadIdx.x >> 5, q = (threadIdx.x & 31) >> 2;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    j = tx * 8 + (warp & 1) * 4 + (q & 3);
+    i = ty * 8 + (warp >> 1) * 2 + (q >> 2);
+}
+
+__global__ void __launch_bounds__(kRmThreads)
+raymarch_fwd_kernel(const float4* __restrict__ feat, const float* __restrict__ dens, const int* __restrict__ view2vol,
+                    const float* __restrict__ cam12, const float* __restrict__ zs_g, float4* __restrict__ out_feat,
+                    float* __restrict__ out_sil, float* __restrict__ out_depth, int D, int H, int W, int Sh, int Sw,
+                    int P, int tiles_x) {
+    __shared__ float zs[kMaxP];
+    __shared__ float cam[12];
+    const int n = blockIdx.y;
+    for (int k = threadIdx.x; k < P; k += kRmThreads) zs[k] = zs_g[k];
+    if (threadIdx.x < 12) cam[threadIdx.x] = cam12[n * 12 + threadIdx.x];
+    __syncthreads();
+
+    const int c = threadIdx.x & 3;
+    int i, j;
+    tile_coords(i, j, tiles_x);
+    const bool valid = (i < Sh) && (j < Sw);
+    Ray r = make_ray(cam, i, j, zs, P, D, H, W);
+    if (!valid) r.k1 = 0;
+    // warp-uniform loop bounds (the quad shuffles need every lane of the warp in the loop)
+    int kw0 = r.k1 > r.k0 ? r.k0 : P, kw1 = r.k1 > r.k0 ? r.k1 : 0;
+#pragma unroll
+    for (int s = 16; s >= 4; s >>= 1) {
+        kw0 = min(kw0, __shfl_xor_sync(0xffffffffu, kw0, s));
+        kw1 = max(kw1, __shfl_xor_sync(0xffffffffu, kw1, s));
+    }
+
+    const long long vol = static_cast<long long>(view2vol[n]) * D * H * W;
+    const float4* fv = feat + vol * 4 + c;   // 4 float4 per voxel
+    const float* dv = dens + vol;
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float T = 1.f, depth = 0.f;
+    for (int k = kw0; k < kw1; ++k) {
+        const bool act = (k >= r.k0) && (k < r.k1);
+        const float z = zs[k];
+        Tri t = sample_tri(r, z, D, H, W);
+        if (!act) t.mask = 0;
+        const float sigma = quad_density(t, dv, H, W, c);
+        const float wk = sigma * T;
+        if (wk != 0.f) {
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int cn = 0; cn < 8; ++cn) {
+                if ((t.mask >> cn) & 1u) {
+                    const long long vox =
+                        (static_cast<long long>(t.z0 + (cn >> 2)) * H + (t.y0 + ((cn >> 1) & 1))) * W + (t.x0 + (cn & 1));
+                    const float4 val = __ldg(fv + vox * 4);
+                    const float w = tri_weight(t, cn);
+                    f.x = fmaf(val.x, w, f.x);
+                    f.y = fmaf(val.y, w, f.y);
+                    f.z = fmaf(val.z, w, f.z);
+                    f.w = fmaf(val.w, w, f.w);
+                }
+            }
+            acc.x = fmaf(wk, f.x, acc.x);
+            acc.y = fmaf(wk, f.y, acc.y);
+            acc.z = fmaf(wk, f.z, acc.z);
+            acc.w = fmaf(wk, f.w, acc.w);
+            depth = fmaf(wk, z, depth);
+        }
+        T = T * (1.f - sigma);
+    }
+    if (valid) {
+        const long long pix = (static_cast<long long>(n) * Sh + i) * Sw + j;
+        out_feat[pix * 4 + c] = acc;
+        if (c == 0) {
+            out_sil[pix] = 1.f - T;
+            if (out_depth) out_depth[pix] = depth;
+        }
+    }
+}
+
+}  // namespace forge
+
+extern "C" int forge_raymarch_fwd(const float* feat_cl, const float* dens, const int* view2vol, const float* cam12,
+                                  const float* zs, float* out_feat, float* out_sil, float* out_depth, int N, int V,
+                                  int D, int H, int W, int S_h, int S_w, int P, void* stream) {
+    using namespace forge;
+    const char* fn = "forge_raymarch_fwd";
+    if (!feat_cl || !dens || !view2vol || !cam12 || !zs || !out_feat || !out_sil) return fail(fn, "null pointer");
+    if (N <= 0 || V <= 0 || S_h <= 0 || S_w <= 0 || P <= 0) return fail(fn, "non-positive size");
+    if (D < 2 || H < 2 || W < 2) return fail(fn, "volume sides must be >= 2");
+    if (P > kMaxP) return fail(fn, "n_pts_per_ray exceeds 512");
+    if (N > 65535) return fail(fn, "more than 65535 views in one launch");
+    if (!aligned16(feat_cl) || !aligned16(out_feat)) return fail(fn, "feat_cl / out_feat must be 16-byte aligned");
+    const int tiles_x = (S_w + 7) / 8, tiles_y = (S_h + 7) / 8;
+    dim3 grid(tiles_x * tiles_y, N);
+    raymarch_fwd_kernel<<<grid, kRmThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(feat_cl), dens, view2vol, cam12, zs, reinterpret_cast<float4*>(out_feat), out_sil,
+        out_depth, D, H, W, S_h, S_w, P, tiles_x);
+    return check_launch(fn);
+}
+
+extern "C" int forge_raymarch_bwd(const float*, const float*, const int*, const float*, const float*, const float*,
+                                  const float*, const float*, float*, float*, float*, int, int, int, int, int, int, int,
+                                  int, void*) {
+    return forge::fail("forge_raymarch_bwd", "not implemented yet");
+}

@@ -1,0 +1,149 @@
+"""VolRender -- drop-in for reference models/volume_render.py (class VolRender, :11-103).
+
+Same constructor, ``forward`` / ``proj_origin`` signatures, return-tuple ordering, ``conv_rgb``
+state_dict keys and in-place halving of the caller's ``K``.  The PyTorch3D camera conversion,
+ray sampler, volume sampler and emission-absorption raymarcher (reference :53-63) are replaced
+by one fused CUDA kernel (``forge_raymarch_fwd/bwd``); the camera algebra that feeds it is a
+dozen tiny differentiable torch ops on [N,3,3] tensors, so gradients reach R, T and K.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+
+def camera_to_cam12(R, T, K_half, vol_dhw, volume_size):
+    """OpenCV extrinsics/intrinsics -> the 12 floats per view the raymarcher consumes.
+
+    Volume-local sample point of pixel (i, j) at depth z:  o + z * M [j+0.5, i+0.5, 1]^T with
+      o = -R^T t / s,   M = diag(1/s) R^T K^-1,   s_axis = (size_axis - 1)/2 * volume_size / D
+    which is what PyTorch3D's NDC un-projection + Volumes.world_to_local produce (reference
+    models/volume_render.py:53-61; derivation in oracle/closed_form.py).
+    """
+    D, H, W = vol_dhw
+    dt, dev = R.dtype, R.device
+    vs = volume_size / D
+    scale = torch.tensor([(W - 1) * 0.5 * vs, (H - 1) * 0.5 * vs, (D - 1) * 0.5 * vs], dtype=dt, device=dev)
+    Rt = R.transpose(1, 2)
+    o = -(Rt @ T.unsqueeze(-1)).squeeze(-1) / scale
+    fx, fy, cx, cy = K_half[:, 0, 0], K_half[:, 1, 1], K_half[:, 0, 2], K_half[:, 1, 2]
+    zero, one = torch.zeros_like(fx), torch.ones_like(fx)
+    Kinv = torch.stack([torch.stack([1.0 / fx, zero, -cx / fx], -1),
+                        torch.stack([zero, 1.0 / fy, -cy / fy], -1),
+                        torch.stack([zero, zero, one], -1)], dim=1)
+    M = (Rt @ Kinv) / scale.view(1, 3, 1)
+    return torch.cat([o, M.reshape(-1, 9)], dim=1)
+
+
+def origin_projection(T, K_half, eps=1e-6):
+    """Pixel (half-res) position of the world origin = cameras.transform_points_screen(0, eps)
+    (reference models/volume_render.py:77-83, :97-103)."""
+    tz = T[:, 2]
+    sign = tz.sign() + (tz == 0).to(tz.dtype)
+    tz = sign * tz.abs().clamp(min=eps)
+    return torch.stack([K_half[:, 0, 0] * T[:, 0] / tz + K_half[:, 0, 2],
+                        K_half[:, 1, 1] * T[:, 1] / tz + K_half[:, 1, 2]], dim=-1)
+
+
+class VolRender(nn.Module):
+    def __init__(self, config):
+        super(VolRender, self).__init__()
+        self.img_size = config.dataset.img_size
+        self.volume_physical_size = config.render.volume_size
+        self.n_pts_per_ray = config.render.n_pts_per_ray
+        self.min_depth = config.render.min_depth
+        self.max_depth = config.render.max_depth
+
+        # from rendered feature map to rgb (reference :27-37; identical state_dict keys)
+        self.k_size = config.render.k_size
+        self.pad_size = self.k_size // 2
+        self.conv_rgb = nn.Sequential(
+            nn.ConvTranspose2d(16, 16, kernel_size=self.k_size + 1, stride=2, padding=self.pad_size),
+            nn.BatchNorm2d(16),
+            nn.LeakyReLU(inplace=True),
+            nn.Conv2d(16, 8, kernel_size=self.k_size, stride=1, padding=self.pad_size),
+            nn.BatchNorm2d(8),
+            nn.LeakyReLU(inplace=True),
+            nn.Conv2d(8, 3, kernel_size=self.k_size, stride=1, padding=self.pad_size),
+        )
+        self._zs = {}
+
+    # checkpoints written with older PyTorch3D carry the ray sampler's grid buffer; ignore it
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        for k in [k for k in state_dict if k.startswith(prefix) and k.endswith('_xy_grid')]:
+            state_dict.pop(k)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def _depths(self, device):
+        key = str(device)
+        if key not in self._zs:
+            # same op PyTorch3D's raysampler uses, so the fp32 sample depths are bit-identical
+            self._zs[key] = torch.linspace(self.min_depth, self.max_depth, self.n_pts_per_ray,
+                                           dtype=torch.float32).to(device)
+        return self._zs[key]
+
+    @staticmethod
+    def _halve_K(camera_params):
+        camera_params['K'] /= 2.0                 # in place on the caller's tensor, like the reference
+        camera_params['K'][:, -1, -1] = 1.0
+        return camera_params['K']
+
+    def render_features(self, camera_params, feature_3d, density_3d, render_depth=False, view2vol=None):
+        """The part of ``forward`` PyTorch3D used to do: -> (feat [N,S,S,16], sil [N,S,S], depth|None,
+        R, T, K_half on the volume's device).  ``view2vol`` (int [N]) lets the caller pass V distinct
+        volumes instead of one materialised copy per view (reference models/model.py:138-139)."""
+        if not feature_3d.is_cuda:
+            raise RuntimeError("forge_b200.VolRender needs CUDA volumes; there is no CPU path")
+        device = feature_3d.device
+        K = self._halve_K(camera_params).to(device)
+        R = camera_params['R'].to(device)
+        T = camera_params['T'].to(device)
+        N = R.shape[0]
+        if view2vol is None:
+            if feature_3d.shape[0] != N or density_3d.shape[0] != N:
+                raise ValueError("Input volumes have to have the same batch size as rays.")
+            if N > 1 and feature_3d.stride(0) == 0 and density_3d.stride(0) == 0:   # expand()-ed single volume
+                feature_3d, density_3d = feature_3d[:1], density_3d[:1]
+                view2vol = torch.zeros(N, dtype=torch.int32, device=device)
+            else:
+                view2vol = torch.arange(N, dtype=torch.int32, device=device)
+        else:
+            view2vol = view2vol.to(device=device, dtype=torch.int32)
+        _, C, D, H, W = feature_3d.shape
+        feat_cl = ops.to_channels_last(feature_3d)
+        dens = density_3d.reshape(density_3d.shape[0], D, H, W)
+        cam12 = camera_to_cam12(R.float(), T.float(), K.float(), (D, H, W), self.volume_physical_size)
+        S = self.img_size // 2
+        feat, sil, depth = ops.raymarch(feat_cl, dens, cam12, view2vol, self._depths(device), S, S, render_depth)
+        return feat, sil, depth, R, T, K
+
+    def forward(self, camera_params, feature_3d, density_3d, render_depth=False, return_origin_proj=False,
+                view2vol=None):
+        '''
+        camera_params: dict with 'R' [B,3,3], 'T' [B,3], 'K' [B,3,3] (OpenCV); K is halved IN PLACE
+        feature_3d: [B,C,D,H,W]
+        density_3d: [B,1,D,H,W]
+        '''
+        feat, sil, depth, R, T, K = self.render_features(camera_params, feature_3d, density_3d, render_depth, view2vol)
+        rendered_imgs = feat.permute(0, 3, 1, 2)                      # NCHW view of the NHWC kernel output
+        rendered_imgs = F.relu(self.conv_rgb(rendered_imgs))
+        rendered_silhouettes = F.interpolate(sil.unsqueeze(1), size=[self.img_size] * 2, mode='bilinear')
+        if render_depth:
+            rendered_depth = F.interpolate(depth.unsqueeze(1), size=[self.img_size] * 2, mode='bilinear')
+
+        if return_origin_proj:
+            origin_proj = origin_projection(T.float(), K.float())
+            if render_depth:
+                return rendered_imgs, rendered_silhouettes, rendered_depth, origin_proj
+            else:
+                return rendered_imgs, rendered_silhouettes, origin_proj
+        else:
+            if render_depth:
+                return rendered_imgs, rendered_silhouettes, rendered_depth
+            else:
+                return rendered_imgs, rendered_silhouettes
+
+    def proj_origin(self, camera_params, device):
+        K = self._halve_K(camera_params).to(device)
+        return origin_projection(camera_params['T'].to(device).float(), K.float())    # in pixel space

@@ -1,0 +1,169 @@
+"""torch-facing wrappers of the C ABI: layout helpers and the two autograd Functions.
+
+torch is used for device memory, streams and autograd bookkeeping only; all arithmetic on
+volumes and images happens in libforge_b200.so.  CUDA tensors are mandatory.
+"""
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("forge_b200 runs on CUDA (sm_100a) only; got a %s tensor. "
+                               "There is no CPU fallback." % t.device)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ---- layout -----------------------------------------------------------------------------------
+def to_channels_last(x):
+    """[n, C, *spatial] (any strides) -> contiguous [n, *spatial, C]; zero-copy when x already is
+    channels-last in memory, otherwise one pass of the re-layout kernel."""
+    _require_cuda(x)
+    perm = (0,) + tuple(range(2, x.dim())) + (1,)
+    xp = x.permute(perm)
+    if xp.is_contiguous() and x.dtype == torch.float32:
+        return xp
+    x = _f32c(x)
+    n, C = x.shape[0], x.shape[1]
+    S = x[0, 0].numel()
+    out = torch.empty([n] + list(x.shape[2:]) + [C], dtype=torch.float32, device=x.device)
+    if C == 1:
+        out.copy_(x.permute(perm))
+        return out
+    with torch.cuda.device(x.device):
+        _lib.call("forge_ncs_to_nsc", _ptr(x), _ptr(out), n, C, S, _stream(x))
+    return out
+
+
+def from_channels_last(x_cl):
+    """contiguous [n, *spatial, C] -> contiguous [n, C, *spatial] with the re-layout kernel."""
+    _require_cuda(x_cl)
+    x_cl = _f32c(x_cl)
+    n, C = x_cl.shape[0], x_cl.shape[-1]
+    S = x_cl[0, ..., 0].numel()
+    out = torch.empty([n, C] + list(x_cl.shape[1:-1]), dtype=torch.float32, device=x_cl.device)
+    with torch.cuda.device(x_cl.device):
+        _lib.call("forge_nsc_to_ncs", _ptr(x_cl), _ptr(out), n, C, S, _stream(x_cl))
+    return out
+
+
+def sample_points(pts, D, H, W, align_corners):
+    """Test hook: base voxel indices [M,3] (x,y,z) and 8-bit in-bounds masks [M] of the device samplers."""
+    _require_cuda(pts)
+    pts = _f32c(pts.reshape(-1, 3))
+    M = pts.shape[0]
+    base = torch.empty(M, 3, dtype=torch.int32, device=pts.device)
+    mask = torch.empty(M, dtype=torch.uint8, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _lib.call("forge_sample_points", _ptr(pts), M, D, H, W, int(bool(align_corners)), _ptr(base), _ptr(mask),
+                  _stream(pts))
+    return base, mask
+
+
+# ---- K1 ---------------------------------------------------------------------------------------
+class _Raymarch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat_cl, dens, cam12, view2vol, zs, S_h, S_w, render_depth):
+        N = cam12.shape[0]
+        V, D, H, W, C = feat_cl.shape
+        dev = feat_cl.device
+        out = torch.empty(N, S_h, S_w, C, dtype=torch.float32, device=dev)
+        sil = torch.empty(N, S_h, S_w, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, S_h, S_w, dtype=torch.float32, device=dev) if render_depth else None
+        with torch.cuda.device(dev):
+            _lib.call("forge_raymarch_fwd", _ptr(feat_cl), _ptr(dens), _ptr(view2vol), _ptr(cam12), _ptr(zs),
+                      _ptr(out), _ptr(sil), _ptr(depth), N, V, D, H, W, S_h, S_w, zs.numel(), _stream(feat_cl))
+        ctx.save_for_backward(feat_cl, dens, cam12, view2vol, zs)
+        ctx.dims = (N, V, D, H, W, S_h, S_w)
+        ctx.render_depth = render_depth
+        if render_depth:
+            return out, sil, depth
+        dummy = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(dummy)
+        return out, sil, dummy
+
+    @staticmethod
+    def backward(ctx, g_out, g_sil, g_depth):
+        feat_cl, dens, cam12, view2vol, zs = ctx.saved_tensors
+        N, V, D, H, W, S_h, S_w = ctx.dims
+        dev = feat_cl.device
+        need_f, need_d, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        g_out = torch.zeros(N, S_h, S_w, feat_cl.shape[-1], device=dev) if g_out is None else _f32c(g_out)
+        g_sil = torch.zeros(N, S_h, S_w, device=dev) if g_sil is None else _f32c(g_sil)
+        g_depth = _f32c(g_depth) if (ctx.render_depth and g_depth is not None) else None
+        gf = torch.zeros_like(feat_cl) if need_f else None
+        gd = torch.zeros_like(dens) if need_d else None
+        gc = torch.zeros_like(cam12) if need_c else None
+        if need_f or need_d or need_c:
+            with torch.cuda.device(dev):
+                _lib.call("forge_raymarch_bwd", _ptr(feat_cl), _ptr(dens), _ptr(view2vol), _ptr(cam12), _ptr(zs),
+                          _ptr(g_out), _ptr(g_sil), _ptr(g_depth), _ptr(gf), _ptr(gd), _ptr(gc),
+                          N, V, D, H, W, S_h, S_w, zs.numel(), _stream(feat_cl))
+        return gf, gd, gc, None, None, None, None, None
+
+
+def raymarch(feat_cl, dens, cam12, view2vol, zs, S_h, S_w, render_depth=False):
+    """feat_cl [V,D,H,W,16], dens [V,D,H,W], cam12 [N,12], view2vol int32 [N], zs [P]
+    -> feat image [N,S_h,S_w,16], silhouette [N,S_h,S_w], depth [N,S_h,S_w] or None."""
+    _require_cuda(feat_cl, dens, cam12, view2vol, zs)
+    if feat_cl.shape[-1] != 16:
+        raise ValueError("the render feature volume must have 16 channels (got %d)" % feat_cl.shape[-1])
+    if dens.shape != feat_cl.shape[:-1]:
+        raise ValueError("density volume %s does not match feature volume %s" % (tuple(dens.shape), tuple(feat_cl.shape)))
+    if cam12.shape[0] != view2vol.numel():
+        raise ValueError("cam12 and view2vol disagree on the number of views")
+    out, sil, depth = _Raymarch.apply(_f32c(feat_cl), _f32c(dens), _f32c(cam12), view2vol.int().contiguous(),
+                                      _f32c(zs), int(S_h), int(S_w), bool(render_depth))
+    return out, sil, (depth if render_depth else None)
+
+
+# ---- K2 ---------------------------------------------------------------------------------------
+class _Rotate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vox_cl, affine12, jobs, gx, gy, gz, gmax, n_dst):
+        n_src, D, H, W, C = vox_cl.shape
+        M = jobs.shape[0]
+        out = torch.empty(n_dst, D, H, W, C, dtype=torch.float32, device=vox_cl.device)
+        with torch.cuda.device(vox_cl.device):
+            _lib.call("forge_rotate_fwd", _ptr(vox_cl), _ptr(affine12), _ptr(jobs), _ptr(gx), _ptr(gy), _ptr(gz),
+                      float(gmax), _ptr(out), M, C, D, H, W, _stream(vox_cl))
+        ctx.save_for_backward(vox_cl, affine12, jobs, gx, gy, gz)
+        ctx.gmax = float(gmax)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        vox_cl, affine12, jobs, gx, gy, gz = ctx.saved_tensors
+        n_src, D, H, W, C = vox_cl.shape
+        need_v, need_a = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gv = torch.zeros_like(vox_cl) if need_v else None
+        ga = torch.zeros_like(affine12) if need_a else None
+        if need_v or need_a:
+            g_out = _f32c(g_out)
+            with torch.cuda.device(vox_cl.device):
+                _lib.call("forge_rotate_bwd", _ptr(vox_cl), _ptr(affine12), _ptr(jobs), _ptr(gx), _ptr(gy), _ptr(gz),
+                          ctx.gmax, _ptr(g_out), _ptr(gv), _ptr(ga), jobs.shape[0], C, D, H, W, _stream(vox_cl))
+        return gv, ga, None, None, None, None, None, None
+
+
+def rotate_resample(vox_cl, affine12, jobs, gx, gy, gz, gmax, n_dst):
+    """vox_cl [n_src,D,H,W,C]; affine12 [M,12]; jobs int32 [M,3] = (src, dst, kind) -> [n_dst,D,H,W,C].
+    Every dst slot must be written by exactly one job."""
+    _require_cuda(vox_cl, affine12, jobs, gx, gy, gz)
+    return _Rotate.apply(_f32c(vox_cl), _f32c(affine12), jobs.int().contiguous(), _f32c(gx), _f32c(gy), _f32c(gz),
+                         float(gmax), int(n_dst))

@@ -1,0 +1,98 @@
+/* forge_b200.h -- C ABI of the B200-native FORGE render / rotate hot path.
+ *
+ * The reference (UT-Austin-RPL/FORGE) is pure Python and has no FFI layer; its hot path is the
+ * library-kernel sequence that models/volume_render.py and models/rotate.py trigger through
+ * PyTorch3D / ATen.  Each entry point below replaces one such sequence (cited per function,
+ * paths relative to the reference root).  The Python modules in forge_b200/models/ bind these
+ * with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - return 0 on success, non-zero on error; forge_last_error() gives the thread-local message
+ *   - the caller owns every buffer (device memory unless stated), nothing is allocated, no
+ *     synchronisation, no stream creation: work is enqueued on `stream` (a cudaStream_t)
+ *   - device pointers must be 16-byte aligned; all tensors are dense fp32 / int32
+ *   - "channels-last" volume = [V][D][H][W][C] (C fastest); images are [N][S_h][S_w][C]
+ *   - built for sm_100a only; there is no CPU fallback
+ */
+#ifndef FORGE_B200_H
+#define FORGE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FORGE_ABI_VERSION 3
+#define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
+
+int forge_abi_version(void);
+const char* forge_last_error(void);
+
+/* ---- layout ------------------------------------------------------------------------------
+ * [n][C][S] <-> [n][S][C] transposes (S = D*H*W).  Replaces the strided NCDHW gathers of ATen's
+ * grid_sampler_3d (reached from models/rotate.py:137 and PyTorch3D's VolumeSampler via
+ * models/volume_render.py:63) by one coalesced re-layout per DISTINCT volume. */
+int forge_ncs_to_nsc(const float* src, float* dst, int n, int C, long long S, void* stream);
+int forge_nsc_to_ncs(const float* src, float* dst, int n, int C, long long S, void* stream);
+
+/* ---- K1: fused volume raymarcher ----------------------------------------------------------
+ * Replaces models/volume_render.py:53-63 = PyTorch3D cameras_from_opencv_projection +
+ * NDCGridRaysampler + VolumeSampler (2x grid_sample, align_corners=True, zeros padding) +
+ * EmissionAbsorptionRaymarcher with the depth patch of README.md:26-33.
+ *
+ *   sample point   p(n,i,j,k) = o_n + zs[k] * (M_n . [j+0.5, i+0.5, 1]^T)      (volume-local coords)
+ *   cam12[n]       = { o_n[3], M_n[3][3] row-major }
+ *   compositing    T_0 = 1; w_k = s_k T_k; T_{k+1} = T_k (1 - s_k);
+ *                  feat = sum w_k f_k; sil = 1 - T_P; depth = sum w_k zs[k]
+ *
+ *   feat_cl  [V][D][H][W][16]   dens [V][D][H][W]   view2vol [N] (volume index of each view)
+ *   out_feat [N][S_h][S_w][16]  out_sil [N][S_h][S_w]  out_depth [N][S_h][S_w] or NULL
+ */
+int forge_raymarch_fwd(const float* feat_cl, const float* dens, const int* view2vol, const float* cam12,
+                       const float* zs, float* out_feat, float* out_sil, float* out_depth,
+                       int N, int V, int D, int H, int W, int S_h, int S_w, int P, void* stream);
+
+/* Backward of forge_raymarch_fwd.  g_* are the upstream gradients (g_depth may be NULL).
+ * grad_feat_cl [V][D][H][W][16] and grad_dens [V][D][H][W] are ACCUMULATED into (caller zeroes
+ * them); either may be NULL to skip that gradient (pose-only refinement, reference
+ * kubric_eval.py:450-504).  grad_cam12 [N][12] is accumulated into (caller zeroes), may be NULL.
+ * Replaces the autograd graph PyTorch builds through the sequence named above. */
+int forge_raymarch_bwd(const float* feat_cl, const float* dens, const int* view2vol, const float* cam12,
+                       const float* zs, const float* g_feat, const float* g_sil, const float* g_depth,
+                       float* grad_feat_cl, float* grad_dens, float* grad_cam12,
+                       int N, int V, int D, int H, int W, int S_h, int S_w, int P, void* stream);
+
+/* ---- K2: affine feature-volume resample ---------------------------------------------------
+ * Replaces models/rotate.py:127-141: materialised homogeneous grid, matmul with T^T, divide by
+ * grid_coord_max, F.grid_sample(bilinear, zeros, align_corners=False), and the torch.cat that
+ * passes view 0 through.  One launch performs M jobs:
+ *
+ *   jobs[m] = { src volume, dst volume, kind }   kind 0: resample with affine12[m], kind 1: copy
+ *   sample  g = (affine12[m] . [gx[w], gy[h], gz[d], 1]^T) * (1 / grid_coord_max)
+ *
+ *   vox_cl [n_src][D][H][W][C] -> out_cl [n_dst][D][H][W][C]; gx [W], gy [H], gz [D] are the
+ *   world coordinates of voxel centres (models/rotate.py:48-52).  The dst index lets the caller
+ *   fold the distance-sorted view permutation (models/model.py:152-168) into the resample. */
+int forge_rotate_fwd(const float* vox_cl, const float* affine12, const int* jobs, const float* gx,
+                     const float* gy, const float* gz, float grid_coord_max, float* out_cl,
+                     int M, int C, int D, int H, int W, void* stream);
+
+/* Backward of forge_rotate_fwd.  grad_vox_cl [n_src][D][H][W][C] is accumulated into (caller
+ * zeroes) or NULL; grad_affine12 [M][12] is accumulated into (caller zeroes) or NULL (needs
+ * vox_cl).  Copy jobs add g_out into grad_vox_cl. */
+int forge_rotate_bwd(const float* vox_cl, const float* affine12, const int* jobs, const float* gx,
+                     const float* gy, const float* gz, float grid_coord_max, const float* g_out_cl,
+                     float* grad_vox_cl, float* grad_affine12, int M, int C, int D, int H, int W,
+                     void* stream);
+
+/* ---- test hook: the index path of both samplers -------------------------------------------
+ * For each normalised point pts[m] = (x, y, z) returns the base voxel (floor) index base[m] =
+ * (ix0, iy0, iz0) and an 8-bit in-bounds mask (bit = dz*4 + dy*2 + dx) computed by exactly the
+ * device functions K1 (align_corners=1) and K2 (align_corners=0) use.  Bit-exact contract
+ * against ATen's GridSampler.h unnormalize + floor. */
+int forge_sample_points(const float* pts, int M, int D, int H, int W, int align_corners, int* base,
+                        unsigned char* mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FORGE_B200_H */

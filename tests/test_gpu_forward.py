@@ -1,0 +1,254 @@
+"""GPU parity tests (forward): CUDA path through the C ABI vs the oracle, golden fixtures, KATs.
+
+Tolerances: fp32 images max-abs <= 1e-4 (BASELINE.json north_star); index math bit-exact.
+"""
+import warnings
+
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+from forge_b200 import ops, synthetic as syn            # noqa: E402
+from forge_b200.models.volume_render import VolRender, camera_to_cam12  # noqa: E402
+from forge_b200.models.rotate import Rotate_world      # noqa: E402
+from oracle import reference_path as rp, closed_form as cf   # noqa: E402
+
+DEV = 'cuda'
+TOL = 1e-4
+
+
+def test_library_loads_and_abi():
+    from forge_b200 import _lib
+    lib = _lib.load()
+    assert lib.forge_abi_version() == _lib.ABI_VERSION
+    with pytest.raises(RuntimeError, match="null pointer"):
+        _lib.call("forge_ncs_to_nsc", None, None, 1, 1, 1, None)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 5, 7, 9), (3, 128, 8, 8, 8), (1, 3, 4, 4, 33)])
+def test_relayout_roundtrip_bit_exact(shape):
+    x = torch.randn(*shape, device=DEV)
+    cl = ops.to_channels_last(x)
+    assert cl.shape == (shape[0],) + shape[2:] + (shape[1],)
+    assert torch.equal(cl, x.permute(0, 2, 3, 4, 1).contiguous())
+    assert torch.equal(ops.from_channels_last(cl), x)
+    # already channels-last in memory -> zero copy
+    y = cl.permute(0, 4, 1, 2, 3)
+    assert ops.to_channels_last(y).data_ptr() == cl.data_ptr()
+
+
+@pytest.mark.parametrize("ac", [True, False])
+def test_sampler_index_math_bit_exact(ac):
+    """floor index + in-bounds flags of the device samplers == ATen's formula evaluated in fp32 on CPU."""
+    torch.manual_seed(3)
+    D, H, W = 64, 48, 33
+    pts = torch.cat([torch.rand(200000, 3) * 2.6 - 1.3,
+                     torch.tensor([[-1., -1, -1], [1, 1, 1], [0, 0, 0], [1.0000001, -1.0000001, 0.99999994]]),
+                     (torch.randint(0, 64, (5000, 3)).float() / 31.5 - 1)])   # many exact-integer hits
+    base, mask = ops.sample_points(pts.to(DEV), D, H, W, ac)
+    size = torch.tensor([W, H, D], dtype=torch.float32)
+    if ac:
+        idx = ((pts + 1.0) / 2) * (size - 1)            # GridSampler.h:27-36, align_corners=True
+    else:
+        idx = ((pts + 1.0) * size - 1) / 2
+    b = torch.floor(idx).to(torch.int32)
+    assert torch.equal(base.cpu(), b)
+    lim = torch.tensor([W, H, D], dtype=torch.int32)
+    in0 = (b >= 0) & (b < lim)
+    in1 = (b + 1 >= 0) & (b + 1 < lim)
+    m = torch.zeros(len(pts), dtype=torch.int32)
+    for c in range(8):
+        ok = (in1[:, 0] if c & 1 else in0[:, 0]) & (in1[:, 1] if c & 2 else in0[:, 1]) & (in1[:, 2] if c & 4 else in0[:, 2])
+        m |= ok.int() << c
+    assert torch.equal(mask.cpu().int(), m)
+
+
+def _module_from_golden(g):
+    cfg = syn.make_config(img_size=g['img_size'], n_pts_per_ray=g['n_pts'], min_depth=g['min_depth'],
+                          max_depth=g['max_depth'], volume_size=g['volume_size'])
+    m = VolRender(cfg)
+    m.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd.')}, strict=True)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("name", ["volrender_small", "volrender_dense"])
+def test_volrender_matches_reference_golden(name):
+    g = load_golden(name)
+    m = _module_from_golden(g)
+    idx = g['view2vol'].long()
+    cam = dict(R=g['R'].clone(), T=g['T'].clone(), K=g['K'].clone())          # CPU cameras, CUDA volumes
+    with torch.no_grad():
+        feat, sil, depth, _, _, _ = m.render_features(cam, g['feat'][idx].to(DEV), g['dens'][idx].to(DEV), True)
+    core = g['core'].to(DEV)
+    assert (feat - core[..., :16]).abs().max().item() <= TOL
+    assert (sil - core[..., 16]).abs().max().item() <= TOL
+    assert (depth - core[..., 17]).abs().max().item() <= TOL
+    assert torch.allclose(cam['K'][:, 0, 0], g['K'][:, 0, 0] / 2) and bool((cam['K'][:, 2, 2] == 1).all())
+    # full forward through the public module API, as-called (one volume per view) and de-duplicated
+    for dedup in (False, True):
+        cam = dict(R=g['R'].clone(), T=g['T'].clone(), K=g['K'].clone())
+        with torch.no_grad():
+            if dedup:
+                out = m(cam, g['feat'].to(DEV), g['dens'].to(DEV), render_depth=True, return_origin_proj=True,
+                        view2vol=g['view2vol'])
+            else:
+                out = m(cam, g['feat'][idx].to(DEV), g['dens'][idx].to(DEV), render_depth=True, return_origin_proj=True)
+        rgb, sil2, depth2, op = out
+        assert rgb.shape == g['rgb'].shape and sil2.shape == g['sil'].shape
+        assert (rgb.cpu() - g['rgb']).abs().max().item() <= TOL
+        assert (sil2.cpu() - g['sil']).abs().max().item() <= TOL
+        assert (depth2.cpu() - g['depth']).abs().max().item() <= TOL
+        assert (op.cpu() - g['origin_proj']).abs().max().item() <= 1e-3   # pixels
+    # return-tuple ordering of the other flag combinations (models/volume_render.py:77-88)
+    cam = dict(R=g['R'].clone(), T=g['T'].clone(), K=g['K'].clone())
+    with torch.no_grad():
+        assert len(m(cam, g['feat'][idx].to(DEV), g['dens'][idx].to(DEV))) == 2
+        cam = dict(R=g['R'].clone(), T=g['T'].clone(), K=g['K'].clone())
+        o3 = m(cam, g['feat'][idx].to(DEV), g['dens'][idx].to(DEV), return_origin_proj=True)
+        assert len(o3) == 3 and o3[2].shape == (len(idx), 2)
+
+
+def _raymarch_vs_oracle(n_obj, n_views, img, vol, P, dense, seed=0, oracle_dev='cpu'):
+    inp = syn.render_inputs(n_obj, n_views, img, vol, seed=seed, dense=dense)
+    cfg = syn.make_config(img_size=img, n_pts_per_ray=P)
+    m = VolRender(cfg).to(DEV).eval()
+    cam = dict(R=inp['R'].clone(), T=inp['T'].clone(), K=inp['K'].clone())
+    with torch.no_grad():
+        feat, sil, depth, _, _, Kh = m.render_features(cam, inp['feat'].to(DEV), inp['dens'].to(DEV), True,
+                                                       view2vol=inp['view2vol'])
+    idx = inp['view2vol'].long()
+    od = oracle_dev
+    worst = 0.0
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for b in range(n_obj):      # one object at a time keeps the oracle's [N,S,S,P,16] intermediates small
+            sel = (idx == b).nonzero().squeeze(1)
+            ren = rp.make_renderer(img, P, cfg.render.min_depth, cfg.render.max_depth)
+            camb = dict(R=inp['R'][sel].to(od), T=inp['T'][sel].to(od), K=inp['K'][sel].clone().to(od))
+            core, _ = rp.raymarch_core(ren, camb, inp['feat'][b:b + 1].expand(len(sel), -1, -1, -1, -1).to(od),
+                                       inp['dens'][b:b + 1].expand(len(sel), -1, -1, -1, -1).to(od), img, 1.0, True)
+            core = core.to(DEV)
+            worst = max(worst, (feat[sel] - core[..., :16]).abs().max().item(),
+                        (sil[sel] - core[..., 16]).abs().max().item(), (depth[sel] - core[..., 17]).abs().max().item())
+    return worst, sil
+
+
+def test_raymarch_cfg1_vs_oracle():
+    """BASELINE.json configs[0]: 1 object, 5 views 64x64 (img 128), 32^3 voxels, 32 samples."""
+    worst, sil = _raymarch_vs_oracle(1, 5, 128, 32, 32, dense=False)
+    assert worst <= TOL, worst
+    assert sil.max().item() > 0.5       # the rays do hit the volume
+
+
+def test_raymarch_cfg1_dense_sigma_gt_1():
+    """relu(randn)*1.5 densities: sign-alternating transmittance must be reproduced."""
+    worst, sil = _raymarch_vs_oracle(1, 5, 128, 32, 32, dense=True, seed=4)
+    assert sil.min().item() < -0.05 or sil.max().item() > 1.05      # 1-prod(1-s) left [0,1]
+    assert worst <= 5e-4, worst      # values grow like prod|1-s|; tolerance scaled accordingly
+
+
+def test_raymarch_cfg2_vs_oracle():
+    """BASELINE.json configs[1]: 4 objects x 5 views 128x128 (img 256), 64^3 voxels, 64 samples."""
+    worst, _ = _raymarch_vs_oracle(4, 5, 256, 64, 64, dense=False, seed=1, oracle_dev=DEV)
+    assert worst <= TOL, worst
+
+
+def test_raymarch_ragged_image_and_views_outside():
+    """Image side not a multiple of the 8x8 tile, plus a camera that looks away from the volume."""
+    inp = syn.render_inputs(1, 3, 2 * 21, 9, seed=7)
+    inp['R'][2] = inp['R'][2] @ torch.diag(torch.tensor([-1.0, 1.0, -1.0]))   # turn the camera around
+    cfg = syn.make_config(img_size=42, n_pts_per_ray=19)
+    m = VolRender(cfg).to(DEV).eval()
+    cam = dict(R=inp['R'].clone(), T=inp['T'].clone(), K=inp['K'].clone())
+    with torch.no_grad():
+        feat, sil, depth, _, _, Kh = m.render_features(cam, inp['feat'].to(DEV), inp['dens'].to(DEV), True,
+                                                       view2vol=inp['view2vol'])
+        f, o, d = cf.raymarch(inp['R'], inp['T'], Kh.cpu(), inp['feat'].expand(3, -1, -1, -1, -1),
+                              inp['dens'].expand(3, -1, -1, -1, -1), 21, 19, 0.5, 2.0, 1.0)
+    assert (feat.cpu() - f).abs().max().item() <= TOL
+    assert (sil.cpu() - o).abs().max().item() <= TOL
+    assert (depth.cpu() - d).abs().max().item() <= TOL
+    assert sil[2].abs().max().item() == 0.0 and feat[2].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("sigma", [0.25, 1.0, 2.0])
+def test_kat_constant_volume(sigma):
+    P, D, S = 8, 8, 8
+    feat = torch.full((1, 16, D, D, D), 0.5, device=DEV)
+    dens = torch.full((1, 1, D, D, D), sigma, device=DEV)
+    R, T, _ = syn.ring_cameras(1)
+    cfg = syn.make_config(img_size=2 * S, n_pts_per_ray=P, max_depth=1.9)
+    m = VolRender(cfg).to(DEV)
+    with torch.no_grad():
+        f, o, d, _, _, _ = m.render_features(dict(R=R, T=T, K=syn.intrinsics(1, 2 * S)), feat, dens, True)
+    Kh = (syn.intrinsics(1, 2 * S) / 2).double()
+    Kh[:, 2, 2] = 1.0
+    fo, oo, do = cf.raymarch(R.double(), T.double(), Kh, feat.cpu().double(), dens.cpu().double(), S, P, 0.5, 1.9, 1.0)
+    assert (o.cpu().double() - oo).abs().max().item() <= 1e-5 * max(1.0, abs(1 - sigma) ** P)
+    assert (f.cpu().double() - fo).abs().max().item() <= 1e-5 * max(1.0, abs(1 - sigma) ** P)
+    if sigma == 1.0:
+        assert (d.cpu().double() - do).abs().max().item() <= 1e-5
+
+
+# ---- K2 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rotate_g16", "rotate_g32"])
+def test_rotate_matches_reference_golden(name):
+    g = load_golden(name)
+    m = Rotate_world(syn.make_config()).to(DEV)
+    with torch.no_grad():
+        out = m(g['voxels'].to(DEV), g['poses'].to(DEV), grid_size=g['grid'])
+    assert out.shape == g['out'].shape
+    assert (out.cpu() - g['out']).abs().max().item() <= TOL
+    assert torch.equal(out[:, 0].cpu(), g['voxels'][:, 0])
+    gm = torch.tensor([m.grid_coord_max_16, m.grid_coord_max, m.grid_coord_max_48, m.grid_coord_max_64,
+                       m.grid_coord_max_128], dtype=torch.float64)
+    assert torch.equal(gm, g['grid_coord_max'])
+
+
+def test_rotate_kat_identity_shrinks_borders():
+    m = Rotate_world(syn.make_config()).to(DEV)
+    ones = torch.ones(1, 2, 4, 32, 32, 32, device=DEV)
+    eye = torch.eye(4, device=DEV).repeat(1, 2, 1, 1)
+    r = m(ones, eye, grid_size=32)[0, 1, 0]
+    assert r[5, 5, 5].item() == pytest.approx(1.0, abs=1e-6)
+    assert r[0, 5, 5].item() == pytest.approx(0.5, abs=1e-6)
+    assert r[0, 0, 5].item() == pytest.approx(0.25, abs=1e-6)
+    assert r[0, 0, 0].item() == pytest.approx(0.125, abs=1e-6)
+
+
+@pytest.mark.parametrize("B,t,C,n", [(2, 5, 128, 32), (1, 5, 128, 16), (1, 3, 16, 48), (1, 2, 6, 20)])
+def test_rotate_vs_oracle(B, t, C, n):
+    vox, poses = syn.rotate_inputs(B, t, C, n, seed=5)
+    m = Rotate_world(syn.make_config()).to(DEV)
+    with torch.no_grad():
+        out = m(vox.to(DEV), poses.to(DEV), grid_size=n)
+        ref = rp.rotate_world_forward(vox.to(DEV), poses.to(DEV), n, 1.0)      # same ATen ops as the reference, on GPU
+    assert (out - ref).abs().max().item() <= TOL
+    # layouts: channels-last input gives the same answer without the re-layout pass
+    vox_cl = vox.to(DEV).permute(0, 1, 3, 4, 5, 2).contiguous().permute(0, 1, 5, 2, 3, 4)
+    with torch.no_grad():
+        out2 = m(vox_cl, poses.to(DEV), grid_size=n)
+    assert torch.equal(out, out2)
+
+
+def test_rotate_order_folds_view_permutation():
+    """order= reproduces chose_selected(rotate(x), sequence_from_distance(...)) (models/model.py:128-129)."""
+    vox, poses = syn.rotate_inputs(2, 5, 16, 16, seed=6)
+    m = Rotate_world(syn.make_config()).to(DEV)
+    idxs = rp.sequence_from_distance(poses[:, :, :3, 3])
+    with torch.no_grad():
+        plain = m(vox.to(DEV), poses.to(DEV), grid_size=16)
+        folded = m(vox.to(DEV), poses.to(DEV), grid_size=16, order=idxs)
+    assert torch.equal(folded, rp.chose_selected(plain, idxs.to(DEV)))
+
+
+def test_cpu_inputs_fail_loudly():
+    m = VolRender(syn.make_config(img_size=16, n_pts_per_ray=4))
+    inp = syn.render_inputs(1, 1, 16, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(dict(R=inp['R'], T=inp['T'], K=inp['K']), inp['feat'], inp['dens'])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Rotate_world(syn.make_config())(torch.zeros(1, 2, 4, 8, 8, 8), torch.eye(4).repeat(1, 2, 1, 1), grid_size=8)

@@ -1,0 +1,163 @@
+#!/usr/bin/env python
+"""Per-kernel timings on one B200 (development aid; bench.py is the contract benchmark).
+
+    python tools/bench_kernels.py [--reps 20] [--ref] [--only k1|k2|...]
+
+Prints one JSON line per measurement: kernel, ms, achieved GB/s on ALGORITHMIC bytes, fraction of
+the measured HBM peak.  L2 is flushed before every timed launch.  --ref also times the oracle
+(the reference's PyTorch3D / ATen op sequence) on the same GPU: the denominator of the ">= 10x
+the reference GPU renderer" target in BASELINE.json.
+"""
+import argparse
+import json
+import os
+import sys
+import warnings
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from forge_b200 import ops, synthetic as syn                     # noqa: E402
+from forge_b200.models.volume_render import VolRender, camera_to_cam12   # noqa: E402
+from forge_b200.models.rotate import Rotate_world                # noqa: E402
+
+DEV = torch.device('cuda')
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p))["hbm_gbs"] if os.path.exists(p) else 6650.0
+
+
+def timeit(fn, reps, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def report(name, ms, best, nbytes=None, **kw):
+    d = {"kernel": name, "ms_median": round(ms, 4), "ms_best": round(best, 4)}
+    if nbytes:
+        d["algorithmic_MB"] = round(nbytes / 1e6, 2)
+        d["GBps"] = round(nbytes / ms / 1e6, 1)
+        d["hbm_frac"] = round(nbytes / ms / 1e6 / peak(), 4)
+    d.update(kw)
+    print(json.dumps(d), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--ref", action="store_true")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--objects", type=int, default=4)
+    ap.add_argument("--img", type=int, default=256)
+    ap.add_argument("--vol", type=int, default=64)
+    ap.add_argument("--pts", type=int, default=64)
+    ap.add_argument("--bwd", action="store_true")
+    args = ap.parse_args()
+    want = lambda k: (not args.only) or k in args.only.split(",")   # noqa: E731
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=DEV)
+    b, t, img, D, P = args.objects, 5, args.img, args.vol, args.pts
+    S = img // 2
+    N = b * t
+    rays = N * S * S
+    inp = syn.render_inputs(b, t, img, D, seed=0, device=DEV)
+    cfg = syn.make_config(img_size=img, n_pts_per_ray=P)
+    m = VolRender(cfg).to(DEV).eval()
+    Kh = inp['K'].clone()
+    Kh /= 2
+    Kh[:, 2, 2] = 1
+    cam12 = camera_to_cam12(inp['R'], inp['T'], Kh, (D, D, D), 1.0).contiguous()
+    zs = m._depths(DEV)
+    dens4 = inp['dens'].reshape(b, D, D, D)
+    feat_cl = ops.to_channels_last(inp['feat'])
+
+    with torch.no_grad():
+        if want("relayout"):
+            ms, best = timeit(lambda: ops.to_channels_last(inp['feat']), args.reps, flush)
+            report("ncs_to_nsc (feat %dx16x%d^3)" % (b, D), ms, best, 2 * inp['feat'].numel() * 4)
+        if want("k1"):
+            k1_bytes = b * 17 * D ** 3 * 4 + rays * 18 * 4 + N * 48
+            ms, best = timeit(lambda: ops.raymarch(feat_cl, dens4, cam12, inp['view2vol'], zs, S, S, True), args.reps, flush)
+            report("raymarch_fwd", ms, best, k1_bytes, Mrays_per_s=round(rays / ms / 1e3, 1),
+                   fp32_TFLOPs=round(rays * P * 366 / ms / 1e9, 2))
+        if want("volrender"):
+            def full():
+                cam = dict(R=inp['R'], T=inp['T'], K=inp['K'].clone())
+                return m(cam, inp['feat'], inp['dens'], render_depth=True, return_origin_proj=True, view2vol=inp['view2vol'])
+            ms, best = timeit(full, args.reps, flush)
+            report("VolRender.forward (relayout+K1+conv_rgb cuDNN+upsample)", ms, best, None, Mrays_per_s=round(rays / ms / 1e3, 1))
+        if want("k2"):
+            C, n = 128, D // 2
+            vox, poses = syn.rotate_inputs(b, t, C, n, seed=1, device=DEV)
+            rot = Rotate_world(cfg).to(DEV)
+            vox_cl = vox.permute(0, 1, 3, 4, 5, 2).contiguous().permute(0, 1, 5, 2, 3, 4)
+            k2_bytes = 2 * b * t * C * n ** 3 * 4
+            ms, best = timeit(lambda: rot(vox_cl, poses, grid_size=n), args.reps, flush)
+            report("rotate_fwd channels-last in/out (%dx%dx%dx%d^3)" % (b, t, C, n), ms, best, k2_bytes)
+            ms, best = timeit(lambda: rot(vox, poses, grid_size=n), args.reps, flush)
+            report("rotate_fwd NCDHW in (+relayout)", ms, best, k2_bytes)
+            if args.ref:
+                from oracle import reference_path as rp
+                ms, best = timeit(lambda: rp.rotate_world_forward(vox, poses, n, 1.0), max(3, args.reps // 4), flush)
+                report("REFERENCE rotate (ATen grid_sample path) on GPU", ms, best, k2_bytes)
+        if args.ref and want("k1"):
+            from oracle import reference_path as rp
+            ren = rp.make_renderer(img, P, 0.5, 2.0).to(DEV)
+            idx = inp['view2vol'].long()
+            fa, da = inp['feat'][idx], inp['dens'][idx]      # as-called: one materialised volume per view
+
+            def ref():
+                cam = dict(R=inp['R'], T=inp['T'], K=inp['K'].clone())
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    return rp.raymarch_core(ren, cam, fa, da, img, 1.0, True)
+            ms, best = timeit(ref, max(3, args.reps // 4), flush)
+            report("REFERENCE raymarch core (PyTorch3D op sequence) on GPU", ms, best, None, Mrays_per_s=round(rays / ms / 1e3, 2))
+
+    if args.bwd:
+        feat_g = feat_cl.clone().requires_grad_(True)
+        dens_g = dens4.clone().requires_grad_(True)
+        cam_g = cam12.clone().requires_grad_(True)
+        go = torch.randn(N, S, S, 16, device=DEV)
+        gs = torch.randn(N, S, S, device=DEV)
+
+        def fb(pose_only):
+            f = feat_cl if pose_only else feat_g
+            d = dens4 if pose_only else dens_g
+            o, s, dep = ops.raymarch(f, d, cam_g, inp['view2vol'], zs, S, S, True)
+            torch.autograd.backward([o, s, dep], [go, gs, gs])
+        for po in (False, True):
+            ms, best = timeit(lambda: fb(po), args.reps, flush)
+            report("raymarch fwd+bwd" + (" (pose-only grads)" if po else " (all grads)"), ms, best, None,
+                   Mrays_per_s=round(rays / ms / 1e3, 1))
+        C, n = 128, D // 2
+        vox, poses = syn.rotate_inputs(b, t, C, n, seed=1, device=DEV)
+        rot = Rotate_world(cfg).to(DEV)
+        vox_cl = vox.permute(0, 1, 3, 4, 5, 2).contiguous().permute(0, 1, 5, 2, 3, 4).requires_grad_(True)
+        poses_g = poses.clone().requires_grad_(True)
+        g = torch.randn(b, t, n, n, n, C, device=DEV).permute(0, 1, 5, 2, 3, 4)
+
+        def rfb():
+            out = rot(vox_cl, poses_g, grid_size=n)
+            out.backward(g)
+        ms, best = timeit(rfb, args.reps, flush)
+        report("rotate fwd+bwd (all grads)", ms, best, 4 * b * t * C * n ** 3 * 4)
+
+
+if __name__ == "__main__":
+    main()
