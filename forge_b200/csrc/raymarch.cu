@@ -165,6 +165,181 @@ raymarch_fwd_kernel(const float4* __restrict__ feat, const float* __restrict__ d
     }
 }
 
+
+// ---- backward ------------------------------------------------------------------------------------
+// With a_k = g_F . f_k + g_D z_k, T_k = prod_{j<k}(1 - s_j) and the suffix recurrence
+//   B_{P-1} = -g_O,   B_{k-1} = a_k s_k + (1 - s_k) B_k
+// the density gradient is dL/ds_k = T_k (a_k - B_k): no division by (1 - s_k), so s_k = 1 and
+// s_k > 1 are handled exactly like torch.cumprod's backward.  Pass A marches front-to-back
+// (re-fetching the features, scattering grad_feat, stashing s_k, a_k, T_k in shared memory),
+// pass B walks back-to-front (dL/ds_k, grad_dens scatter, d s/d p for the camera gradient).
+// d L / d p_k is accumulated per lane into d L / d o and d L / d dir and reduced once per CTA into
+// the 12 camera floats of the view.
+constexpr int kRaysPerCta = kRmThreads / 4;
+
+__global__ void __launch_bounds__(kRmThreads)
+raymarch_bwd_kernel(const float4* __restrict__ feat, const float* __restrict__ dens, const int* __restrict__ view2vol,
+                    const float* __restrict__ cam12, const float* __restrict__ zs_g, const float4* __restrict__ g_feat,
+                    const float* __restrict__ g_sil, const float* __restrict__ g_depth, float* __restrict__ grad_feat,
+                    float* __restrict__ grad_dens, float* __restrict__ grad_cam, int D, int H, int W, int Sh, int Sw,
+                    int P, int tiles_x) {
+    extern __shared__ float smem[];
+    float* zs = smem;                       // [P]
+    float* cam = zs + P;                    // [12]
+    float* red = cam + 12;                  // [12][8 warps]
+    float* s_sig = red + 12 * (kRmThreads / 32);   // [P][64]
+    float* s_a = s_sig + P * kRaysPerCta;
+    float* s_T = s_a + P * kRaysPerCta;
+
+    const int n = blockIdx.y;
+    for (int k = threadIdx.x; k < P; k += kRmThreads) zs[k] = zs_g[k];
+    if (threadIdx.x < 12) cam[threadIdx.x] = cam12[n * 12 + threadIdx.x];
+    __syncthreads();
+
+    const bool need_feat = grad_feat != nullptr, need_dens = grad_dens != nullptr, need_cam = grad_cam != nullptr;
+    const int c = threadIdx.x & 3, ray = threadIdx.x >> 2;
+    int i, j;
+    tile_coords(i, j, tiles_x);
+    const bool valid = (i < Sh) && (j < Sw);
+    Ray r = make_ray(cam, i, j, zs, P, D, H, W);
+    if (!valid) r.k1 = 0;
+    int kw0 = r.k1 > r.k0 ? r.k0 : P, kw1 = r.k1 > r.k0 ? r.k1 : 0;
+#pragma unroll
+    for (int s = 16; s >= 4; s >>= 1) {
+        kw0 = min(kw0, __shfl_xor_sync(0xffffffffu, kw0, s));
+        kw1 = max(kw1, __shfl_xor_sync(0xffffffffu, kw1, s));
+    }
+
+    const long long vol = static_cast<long long>(view2vol[n]) * D * H * W;
+    const float4* fv = feat + vol * 4 + c;
+    const float* dv = dens + vol;
+    float* gfv = need_feat ? grad_feat + vol * 16 + 4 * c : nullptr;
+    float* gdv = need_dens ? grad_dens + vol : nullptr;
+
+    float4 gF = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gO = 0.f, gD = 0.f;
+    if (valid) {
+        const long long pix = (static_cast<long long>(n) * Sh + i) * Sw + j;
+        gF = g_feat[pix * 4 + c];
+        gO = g_sil[pix];
+        if (g_depth) gD = g_depth[pix];
+    }
+    const float sx = 0.5f * static_cast<float>(W - 1), sy = 0.5f * static_cast<float>(H - 1),
+                sz = 0.5f * static_cast<float>(D - 1);
+    float go0 = 0.f, go1 = 0.f, go2 = 0.f, gd0 = 0.f, gd1 = 0.f, gd2 = 0.f;   // per-lane partials
+
+    // ---- pass A: front to back ----
+    float T = 1.f;
+    for (int k = kw0; k < kw1; ++k) {
+        const bool act = (k >= r.k0) && (k < r.k1);
+        const float z = zs[k];
+        Tri t = sample_tri(r, z, D, H, W);
+        if (!act) t.mask = 0;
+        const float sigma = quad_density(t, dv, H, W, c);
+        const float wk = sigma * T;
+        float a_part = 0.f, gix = 0.f, giy = 0.f, giz = 0.f;
+        if (t.mask) {
+            const bool scatter = need_feat && (wk != 0.f);
+#pragma unroll
+            for (int cn = 0; cn < 8; ++cn) {
+                if ((t.mask >> cn) & 1u) {
+                    const long long vox =
+                        (static_cast<long long>(t.z0 + (cn >> 2)) * H + (t.y0 + ((cn >> 1) & 1))) * W + (t.x0 + (cn & 1));
+                    const float4 val = __ldg(fv + vox * 4);
+                    const float q = fmaf(gF.x, val.x, fmaf(gF.y, val.y, fmaf(gF.z, val.z, gF.w * val.w)));
+                    const float wx = (cn & 1) ? t.wx1 : t.wx0, wy = (cn & 2) ? t.wy1 : t.wy0, wz = (cn & 4) ? t.wz1 : t.wz0;
+                    const float wyz = wy * wz;
+                    const float w = wx * wyz;
+                    a_part = fmaf(w, q, a_part);
+                    gix = fmaf((cn & 1) ? wyz : -wyz, q, gix);
+                    giy = fmaf((cn & 2) ? wx * wz : -(wx * wz), q, giy);
+                    giz = fmaf((cn & 4) ? wx * wy : -(wx * wy), q, giz);
+                    if (scatter) {
+                        const float cw = wk * w;
+                        red_add_v4(gfv + vox * 16, make_float4(cw * gF.x, cw * gF.y, cw * gF.z, cw * gF.w));
+                    }
+                }
+            }
+        }
+        a_part += __shfl_xor_sync(0xffffffffu, a_part, 1);
+        a_part += __shfl_xor_sync(0xffffffffu, a_part, 2);
+        if (act) {
+            if (c == 0) {
+                s_sig[k * kRaysPerCta + ray] = sigma;
+                s_a[k * kRaysPerCta + ray] = fmaf(gD, z, a_part);
+                s_T[k * kRaysPerCta + ray] = T;
+            }
+            const float px = wk * gix * sx, py = wk * giy * sy, pz = wk * giz * sz;
+            go0 += px;
+            go1 += py;
+            go2 += pz;
+            gd0 = fmaf(z, px, gd0);
+            gd1 = fmaf(z, py, gd1);
+            gd2 = fmaf(z, pz, gd2);
+        }
+        T = T * (1.f - sigma);
+    }
+    __syncwarp();
+
+    // ---- pass B: back to front (per-quad loop, no shuffles inside) ----
+    if (need_dens || need_cam) {
+        float Bk = -gO;
+        const int c0 = ((c >> 1) << 2) | ((c & 1) << 1);
+        for (int k = r.k1 - 1; k >= r.k0; --k) {
+            const float sigma = s_sig[k * kRaysPerCta + ray], a = s_a[k * kRaysPerCta + ray], Tk = s_T[k * kRaysPerCta + ray];
+            const float dsig = Tk * (a - Bk);
+            Bk = fmaf(a, sigma, (1.f - sigma) * Bk);
+            const float z = zs[k];
+            const Tri t = sample_tri(r, z, D, H, W);
+            const long long row = (static_cast<long long>(t.z0 + (c >> 1)) * H + (t.y0 + (c & 1))) * W + t.x0;
+            const float wy = (c & 1) ? t.wy1 : t.wy0, wz = (c >> 1) ? t.wz1 : t.wz0;
+            float gix = 0.f, giy = 0.f, giz = 0.f;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                if ((t.mask >> (c0 + dx)) & 1u) {
+                    const float wx = dx ? t.wx1 : t.wx0;
+                    if (need_dens) atomicAdd(gdv + row + dx, dsig * (wx * wy * wz));
+                    if (need_cam) {
+                        const float val = __ldg(dv + row + dx);
+                        gix = fmaf(dx ? wy * wz : -(wy * wz), val, gix);
+                        giy = fmaf((c & 1) ? wx * wz : -(wx * wz), val, giy);
+                        giz = fmaf((c >> 1) ? wx * wy : -(wx * wy), val, giz);
+                    }
+                }
+            }
+            const float px = dsig * gix * sx, py = dsig * giy * sy, pz = dsig * giz * sz;
+            go0 += px;
+            go1 += py;
+            go2 += pz;
+            gd0 = fmaf(z, px, gd0);
+            gd1 = fmaf(z, py, gd1);
+            gd2 = fmaf(z, pz, gd2);
+        }
+    }
+    __syncwarp();
+
+    // ---- camera gradient: 12 floats per view, reduced over the CTA ----
+    if (need_cam) {
+        const float u = static_cast<float>(j) + 0.5f, v = static_cast<float>(i) + 0.5f;
+        float g12[12] = {go0, go1, go2, gd0 * u, gd0 * v, gd0, gd1 * u, gd1 * v, gd1, gd2 * u, gd2 * v, gd2};
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+            float x = valid ? g12[e] : 0.f;
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+            if (lane == 0) red[e * (kRmThreads / 32) + warp] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            float x = 0.f;
+#pragma unroll
+            for (int w = 0; w < kRmThreads / 32; ++w) x += red[threadIdx.x * (kRmThreads / 32) + w];
+            atomicAdd(grad_cam + n * 12 + threadIdx.x, x);
+        }
+    }
+}
+
 }  // namespace forge
 
 extern "C" int forge_raymarch_fwd(const float* feat_cl, const float* dens, const int* view2vol, const float* cam12,
@@ -186,8 +361,33 @@ extern "C" int forge_raymarch_fwd(const float* feat_cl, const float* dens, const
     return check_launch(fn);
 }
 
-extern "C" int forge_raymarch_bwd(const float*, const float*, const int*, const float*, const float*, const float*,
-                                  const float*, const float*, float*, float*, float*, int, int, int, int, int, int, int,
-                                  int, void*) {
-    return forge::fail("forge_raymarch_bwd", "not implemented yet");
+extern "C" int forge_raymarch_bwd(const float* feat_cl, const float* dens, const int* view2vol, const float* cam12,
+                                  const float* zs, const float* g_feat, const float* g_sil, const float* g_depth,
+                                  float* grad_feat_cl, float* grad_dens, float* grad_cam12, int N, int V, int D, int H,
+                                  int W, int S_h, int S_w, int P, void* stream) {
+    using namespace forge;
+    const char* fn = "forge_raymarch_bwd";
+    if (!feat_cl || !dens || !view2vol || !cam12 || !zs || !g_feat || !g_sil) return fail(fn, "null pointer");
+    if (!grad_feat_cl && !grad_dens && !grad_cam12) return 0;
+    if (N <= 0 || V <= 0 || S_h <= 0 || S_w <= 0 || P <= 0) return fail(fn, "non-positive size");
+    if (D < 2 || H < 2 || W < 2) return fail(fn, "volume sides must be >= 2");
+    if (N > 65535) return fail(fn, "more than 65535 views in one launch");
+    if (!aligned16(feat_cl) || !aligned16(g_feat) || (grad_feat_cl && !aligned16(grad_feat_cl)))
+        return fail(fn, "feat_cl / g_feat / grad_feat_cl must be 16-byte aligned");
+    const size_t smem = sizeof(float) * (static_cast<size_t>(P) + 12 + 12 * (kRmThreads / 32) +
+                                         3 * static_cast<size_t>(P) * kRaysPerCta);
+    if (smem > 227 * 1024) return fail(fn, "n_pts_per_ray too large for the backward pass (max 300)");
+    static thread_local size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(raymarch_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        if (e != cudaSuccess) return fail(fn, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+        smem_set = smem;
+    }
+    const int tiles_x = (S_w + 7) / 8, tiles_y = (S_h + 7) / 8;
+    dim3 grid(tiles_x * tiles_y, N);
+    raymarch_bwd_kernel<<<grid, kRmThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(feat_cl), dens, view2vol, cam12, zs, reinterpret_cast<const float4*>(g_feat),
+        g_sil, g_depth, grad_feat_cl, grad_dens, grad_cam12, D, H, W, S_h, S_w, P, tiles_x);
+    return check_launch(fn);
 }

@@ -90,6 +90,109 @@ rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
     }
 }
 
+// ---- backward ------------------------------------------------------------------------------------
+__device__ __forceinline__ void vred(float* addr, float v) { atomicAdd(addr, v); }
+__device__ __forceinline__ void vred(float4* addr, const float4& v) { red_add_v4(reinterpret_cast<float*>(addr), v); }
+__device__ __forceinline__ float vscale(float v, float w) { return v * w; }
+__device__ __forceinline__ float4 vscale(const float4& v, float w) { return make_float4(v.x * w, v.y * w, v.z * w, v.w * w); }
+__device__ __forceinline__ float vdot(float a, float b) { return a * b; }
+__device__ __forceinline__ float vdot(const float4& a, const float4& b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+// grad_vox: scatter g * w_corner with vector REDs (channels-last => contiguous, coalesced).
+// grad_affine: d out/d sample-pos needs the corner values; chain through
+//   ix = ((s+1) size - 1)/2, s = c * inv_max, c = A . [gx, gy, gz, 1]
+// into 12 floats per job, reduced per CTA then one atomicAdd per float.
+template <typename VecT>
+__global__ void __launch_bounds__(kRotThreads)
+rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine, const int* __restrict__ jobs,
+                  const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ gz,
+                  float inv_max, const VecT* __restrict__ g_out, VecT* __restrict__ grad_in,
+                  float* __restrict__ grad_aff, int CU, int D, int H, int W, int tiles_x, int tiles_y) {
+    __shared__ float A[12];
+    __shared__ float red[12][kRotThreads / 32];
+    const int m = blockIdx.y;
+    const RotJob job = {jobs[3 * m], jobs[3 * m + 1], jobs[3 * m + 2]};
+    if (threadIdx.x < 12) A[threadIdx.x] = affine[12 * m + threadIdx.x];
+    __syncthreads();
+    const int tz = blockIdx.x / (tiles_x * tiles_y);
+    const int trem = blockIdx.x - tz * tiles_x * tiles_y;
+    const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    const long long vol = static_cast<long long>(D) * H * W;
+    const VecT* src = in + static_cast<long long>(job.src) * vol * CU;
+    const VecT* go = g_out + static_cast<long long>(job.dst) * vol * CU;
+    VecT* gin = grad_in ? grad_in + static_cast<long long>(job.src) * vol * CU : nullptr;
+    const bool need_aff = (grad_aff != nullptr) && job.kind == 0;
+    const float kx = 0.5f * static_cast<float>(W) * inv_max, ky = 0.5f * static_cast<float>(H) * inv_max,
+                kz = 0.5f * static_cast<float>(D) * inv_max;
+    float ga[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) ga[e] = 0.f;
+
+    for (int e = threadIdx.x; e < kTileVox * CU; e += kRotThreads) {
+        const int v = e / CU, cu = e - v * CU;
+        const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
+        if (w >= W || h >= H || d >= D) continue;
+        const long long o = (static_cast<long long>(d) * H + h) * W + w;
+        const VecT g = go[o * CU + cu];
+        if (job.kind == 1) {
+            if (gin) vred(gin + o * CU + cu, g);
+            continue;
+        }
+        const float gxw = gx[w], gyh = gy[h], gzd = gz[d];
+        const Tri t = rotate_tri(A, gxw, gyh, gzd, inv_max, D, H, W);
+        float gix = 0.f, giy = 0.f, giz = 0.f;
+#pragma unroll
+        for (int cn = 0; cn < 8; ++cn) {
+            if ((t.mask >> cn) & 1u) {
+                const long long vox =
+                    (static_cast<long long>(t.z0 + (cn >> 2)) * H + (t.y0 + ((cn >> 1) & 1))) * W + (t.x0 + (cn & 1));
+                const float wx = (cn & 1) ? t.wx1 : t.wx0, wy = (cn & 2) ? t.wy1 : t.wy0, wz = (cn & 4) ? t.wz1 : t.wz0;
+                if (gin) vred(gin + vox * CU + cu, vscale(g, wx * wy * wz));
+                if (need_aff) {
+                    const float q = vdot(g, __ldg(src + vox * CU + cu));
+                    gix = fmaf((cn & 1) ? wy * wz : -(wy * wz), q, gix);
+                    giy = fmaf((cn & 2) ? wx * wz : -(wx * wz), q, giy);
+                    giz = fmaf((cn & 4) ? wx * wy : -(wx * wy), q, giz);
+                }
+            }
+        }
+        if (need_aff) {
+            const float rx = gix * kx, ry = giy * ky, rz = giz * kz;
+            ga[0] = fmaf(rx, gxw, ga[0]);
+            ga[1] = fmaf(rx, gyh, ga[1]);
+            ga[2] = fmaf(rx, gzd, ga[2]);
+            ga[3] += rx;
+            ga[4] = fmaf(ry, gxw, ga[4]);
+            ga[5] = fmaf(ry, gyh, ga[5]);
+            ga[6] = fmaf(ry, gzd, ga[6]);
+            ga[7] += ry;
+            ga[8] = fmaf(rz, gxw, ga[8]);
+            ga[9] = fmaf(rz, gyh, ga[9]);
+            ga[10] = fmaf(rz, gzd, ga[10]);
+            ga[11] += rz;
+        }
+    }
+    if (grad_aff != nullptr && job.kind == 0) {     // uniform per CTA
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+            float x = ga[e];
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+            if (lane == 0) red[e][warp] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            float x = 0.f;
+#pragma unroll
+            for (int w = 0; w < kRotThreads / 32; ++w) x += red[threadIdx.x][w];
+            atomicAdd(grad_aff + 12 * m + threadIdx.x, x);
+        }
+    }
+}
+
 static int rotate_check(const char* fn, const void* vox, const void* aff, const void* jobs, const void* gx,
                         const void* gy, const void* gz, float gmax, int M, int C, int D, int H, int W) {
     if (!vox || !aff || !jobs || !gx || !gy || !gz) return fail(fn, "null pointer");
@@ -123,7 +226,27 @@ extern "C" int forge_rotate_fwd(const float* vox_cl, const float* affine12, cons
     return check_launch(fn);
 }
 
-extern "C" int forge_rotate_bwd(const float*, const float*, const int*, const float*, const float*, const float*, float,
-                                const float*, float*, float*, int, int, int, int, int, void*) {
-    return forge::fail("forge_rotate_bwd", "not implemented yet");
+extern "C" int forge_rotate_bwd(const float* vox_cl, const float* affine12, const int* jobs, const float* gx,
+                                const float* gy, const float* gz, float grid_coord_max, const float* g_out_cl,
+                                float* grad_vox_cl, float* grad_affine12, int M, int C, int D, int H, int W,
+                                void* stream) {
+    using namespace forge;
+    const char* fn = "forge_rotate_bwd";
+    if (int e = rotate_check(fn, vox_cl, affine12, jobs, gx, gy, gz, grid_coord_max, M, C, D, H, W)) return e;
+    if (!g_out_cl) return fail(fn, "null pointer");
+    if (!grad_vox_cl && !grad_affine12) return 0;
+    const int tiles_x = (W + kTx - 1) / kTx, tiles_y = (H + kTy - 1) / kTy, tiles_z = (D + kTz - 1) / kTz;
+    dim3 grid(tiles_x * tiles_y * tiles_z, M);
+    const float inv_max = 1.0f / grid_coord_max;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (C % 4 == 0 && aligned16(vox_cl) && aligned16(g_out_cl) && (!grad_vox_cl || aligned16(grad_vox_cl))) {
+        rotate_bwd_kernel<float4><<<grid, kRotThreads, 0, st>>>(
+            reinterpret_cast<const float4*>(vox_cl), affine12, jobs, gx, gy, gz, inv_max,
+            reinterpret_cast<const float4*>(g_out_cl), reinterpret_cast<float4*>(grad_vox_cl), grad_affine12, C / 4, D, H,
+            W, tiles_x, tiles_y);
+    } else {
+        rotate_bwd_kernel<float><<<grid, kRotThreads, 0, st>>>(vox_cl, affine12, jobs, gx, gy, gz, inv_max, g_out_cl,
+                                                              grad_vox_cl, grad_affine12, C, D, H, W, tiles_x, tiles_y);
+    }
+    return check_launch(fn);
 }

@@ -30,24 +30,32 @@ def _f32c(t):
 
 
 # ---- layout -----------------------------------------------------------------------------------
+class _ToChannelsLast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        n, C = x.shape[0], x.shape[1]
+        S = x[0, 0].numel()
+        out = torch.empty([n] + list(x.shape[2:]) + [C], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("forge_ncs_to_nsc", _ptr(x), _ptr(out), n, C, S, _stream(x))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return from_channels_last(g)
+
+
 def to_channels_last(x):
     """[n, C, *spatial] (any strides) -> contiguous [n, *spatial, C]; zero-copy when x already is
-    channels-last in memory, otherwise one pass of the re-layout kernel."""
+    channels-last in memory, otherwise one pass of the re-layout kernel (differentiable)."""
     _require_cuda(x)
     perm = (0,) + tuple(range(2, x.dim())) + (1,)
     xp = x.permute(perm)
     if xp.is_contiguous() and x.dtype == torch.float32:
         return xp
-    x = _f32c(x)
-    n, C = x.shape[0], x.shape[1]
-    S = x[0, 0].numel()
-    out = torch.empty([n] + list(x.shape[2:]) + [C], dtype=torch.float32, device=x.device)
-    if C == 1:
-        out.copy_(x.permute(perm))
-        return out
-    with torch.cuda.device(x.device):
-        _lib.call("forge_ncs_to_nsc", _ptr(x), _ptr(out), n, C, S, _stream(x))
-    return out
+    if x.shape[1] == 1:
+        return _f32c(x).reshape([x.shape[0]] + list(x.shape[2:]) + [1])
+    return _ToChannelsLast.apply(_f32c(x))
 
 
 def from_channels_last(x_cl):
