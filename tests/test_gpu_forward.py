@@ -162,7 +162,9 @@ def test_raymarch_cfg2_vs_oracle():
 def test_raymarch_ragged_image_and_views_outside():
     """Image side not a multiple of the 8x8 tile, plus a camera that looks away from the volume."""
     inp = syn.render_inputs(1, 3, 2 * 21, 9, seed=7)
-    inp['R'][2] = inp['R'][2] @ torch.diag(torch.tensor([-1.0, 1.0, -1.0]))   # turn the camera around
+    flip = torch.diag(torch.tensor([-1.0, 1.0, -1.0]))      # same camera centre, optical axis reversed
+    inp['R'][2] = flip @ inp['R'][2]
+    inp['T'][2] = flip @ inp['T'][2]
     cfg = syn.make_config(img_size=42, n_pts_per_ray=19)
     m = VolRender(cfg).to(DEV).eval()
     cam = dict(R=inp['R'].clone(), T=inp['T'].clone(), K=inp['K'].clone())
