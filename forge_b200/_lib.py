@@ -18,13 +18,15 @@ _SIGNATURES = {
     "forge_last_error": (_c.c_char_p, []),
     "forge_ncs_to_nsc": (_c.c_int, [_F, _F, _I, _I, _c.c_longlong, _F]),
     "forge_nsc_to_ncs": (_c.c_int, [_F, _F, _I, _I, _c.c_longlong, _F]),
+    "forge_pack_volume": (_c.c_int, [_F, _I, _F, _F, _F, _I, _I, _I, _I, _F]),
+    "forge_unpack_volume_grad": (_c.c_int, [_F, _F, _I, _I, _I, _I, _I, _F]),
     "forge_raymarch_fwd": (_c.c_int, [_F] * 8 + [_I] * 8 + [_F]),
     "forge_raymarch_bwd": (_c.c_int, [_F] * 11 + [_I] * 8 + [_F]),
     "forge_rotate_fwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F] + [_I] * 5 + [_F]),
     "forge_rotate_bwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F, _F, _F] + [_I] * 5 + [_F]),
     "forge_sample_points": (_c.c_int, [_F, _I, _I, _I, _I, _I, _F, _F, _F]),
 }
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lock = threading.Lock()
 _lib = None

@@ -84,6 +84,93 @@ __global__ void sample_points_kernel(const float* __restrict__ pts, int M, int D
     mask[m] = static_cast<unsigned char>(t.mask);
 }
 
+// ---- render-volume packing -------------------------------------------------------------------------
+// One CTA per padded (z, y) row of one volume: builds the zero-bordered channels-last feature row
+// [W+2][16] (from NCDHW through a shared-memory transpose, or from channels-last directly) and the
+// density-quad row [W+1][4].  HBM-bound: reads V*17*D*H*W*4 bytes, writes ~1.1x + 4x the density.
+constexpr int kPackThreads = 256;
+
+__global__ void __launch_bounds__(kPackThreads)
+pack_volume_kernel(const float* __restrict__ feat, int feat_cl, const float* __restrict__ dens,
+                   float* __restrict__ feat_pad, float4* __restrict__ dens_quad, int D, int H, int W) {
+    extern __shared__ float sm[];
+    const int Wp = W + 2, Hp = H + 2, Wq = W + 1, Hq = H + 1;
+    float* tile = sm;                        // [16][W + 1]
+    float* d0 = sm + 16 * (W + 1);           // [W + 2]  density row (z, y-1... see below), x = -1 .. W
+    float* d1 = d0 + Wp;                     // [W + 2]
+    const int v = blockIdx.y;
+    const int zp = blockIdx.x / Hp, yp = blockIdx.x - zp * Hp;
+    const int z = zp - 1, y = yp - 1;
+    const long long S = static_cast<long long>(D) * H * W;
+    const bool zin = (z >= 0 && z < D);
+    const bool interior = zin && (y >= 0 && y < H);
+
+    if (interior && !feat_cl) {
+        const float* src = feat + static_cast<long long>(v) * 16 * S + (static_cast<long long>(z) * H + y) * W;
+        for (int e = threadIdx.x; e < 16 * W; e += kPackThreads) {
+            const int ch = e / W, x = e - ch * W;
+            tile[ch * (W + 1) + x] = src[static_cast<long long>(ch) * S + x];
+        }
+    }
+    // density rows y (d0) and y + 1 (d1) of plane z, zero outside the volume
+    for (int e = threadIdx.x; e < 2 * Wp; e += kPackThreads) {
+        const int which = e / Wp, xs = e - which * Wp;     // xs = x + 1
+        const int yy = y + which, x = xs - 1;
+        float val = 0.f;
+        if (zin && yy >= 0 && yy < H && x >= 0 && x < W)
+            val = dens[static_cast<long long>(v) * S + (static_cast<long long>(z) * H + yy) * W + x];
+        (which ? d1 : d0)[xs] = val;
+    }
+    __syncthreads();
+
+    float* out = feat_pad + ((static_cast<long long>(v) * (D + 2) + zp) * Hp + yp) * Wp * 16;
+    if (interior) {
+        if (feat_cl) {
+            const float* src = feat + (static_cast<long long>(v) * S + (static_cast<long long>(z) * H + y) * W) * 16;
+            for (int e = threadIdx.x; e < Wp * 16; e += kPackThreads) {
+                const int xp = e >> 4;
+                out[e] = (xp >= 1 && xp <= W) ? src[e - 16] : 0.f;
+            }
+        } else {
+            for (int e = threadIdx.x; e < Wp * 16; e += kPackThreads) {
+                const int xp = e >> 4, ch = e & 15;
+                out[e] = (xp >= 1 && xp <= W) ? tile[ch * (W + 1) + xp - 1] : 0.f;
+            }
+        }
+    } else {
+        for (int e = threadIdx.x; e < Wp * 16; e += kPackThreads) out[e] = 0.f;
+    }
+    if (yp <= H) {   // quad row yq = yp covers y = yp - 1 and y + 1 = yp
+        float4* q = dens_quad + ((static_cast<long long>(v) * (D + 2) + zp) * Hq + yp) * Wq;
+        for (int xq = threadIdx.x; xq < Wq; xq += kPackThreads)
+            q[xq] = make_float4(d0[xq], d0[xq + 1], d1[xq], d1[xq + 1]);
+    }
+}
+
+// gradient of the padded feature volume back to the caller's layout (interior voxels only)
+__global__ void __launch_bounds__(kPackThreads)
+unpack_grad_kernel(const float* __restrict__ grad_pad, float* __restrict__ grad, int out_cl, int D, int H, int W) {
+    extern __shared__ float sm[];
+    float* tile = sm;   // [16][W + 1]
+    const int Wp = W + 2, Hp = H + 2;
+    const int v = blockIdx.y;
+    const int z = blockIdx.x / H, y = blockIdx.x - z * H;
+    const long long S = static_cast<long long>(D) * H * W;
+    const float* src = grad_pad + (((static_cast<long long>(v) * (D + 2) + z + 1) * Hp + y + 1) * Wp + 1) * 16;
+    if (out_cl) {
+        float* dst = grad + (static_cast<long long>(v) * S + (static_cast<long long>(z) * H + y) * W) * 16;
+        for (int e = threadIdx.x; e < W * 16; e += kPackThreads) dst[e] = src[e];
+        return;
+    }
+    for (int e = threadIdx.x; e < W * 16; e += kPackThreads) tile[(e & 15) * (W + 1) + (e >> 4)] = src[e];
+    __syncthreads();
+    float* dst = grad + static_cast<long long>(v) * 16 * S + (static_cast<long long>(z) * H + y) * W;
+    for (int e = threadIdx.x; e < 16 * W; e += kPackThreads) {
+        const int ch = e / W, x = e - ch * W;
+        dst[static_cast<long long>(ch) * S + x] = tile[ch * (W + 1) + x];
+    }
+}
+
 static int transpose_common(const char* fn, bool to_nsc, const float* src, float* dst, int n, int C, long long S,
                             void* stream) {
     if (!src || !dst) return fail(fn, "null pointer");
@@ -128,3 +215,34 @@ int forge_sample_points(const float* pts, int M, int D, int H, int W, int align_
 }
 
 }  // extern "C"
+
+extern "C" int forge_pack_volume(const float* feat, int feat_channels_last, const float* dens, float* feat_pad,
+                                 float* dens_quad, int V, int D, int H, int W, void* stream) {
+    using namespace forge;
+    const char* fn = "forge_pack_volume";
+    if (!feat || !dens || !feat_pad || !dens_quad) return fail(fn, "null pointer");
+    if (V <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(fn, "non-positive size");
+    if (V > 65535) return fail(fn, "more than 65535 volumes in one launch");
+    if (!aligned16(dens_quad)) return fail(fn, "dens_quad must be 16-byte aligned");
+    const size_t smem = sizeof(float) * (16 * (W + 1) + 2 * (W + 2));
+    if (smem > 48 * 1024) return fail(fn, "volume rows longer than 700 voxels are not supported");
+    dim3 grid((D + 2) * (H + 2), V);
+    pack_volume_kernel<<<grid, kPackThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        feat, feat_channels_last, dens, feat_pad, reinterpret_cast<float4*>(dens_quad), D, H, W);
+    return check_launch(fn);
+}
+
+extern "C" int forge_unpack_volume_grad(const float* grad_feat_pad, float* grad_feat, int channels_last, int V, int D,
+                                        int H, int W, void* stream) {
+    using namespace forge;
+    const char* fn = "forge_unpack_volume_grad";
+    if (!grad_feat_pad || !grad_feat) return fail(fn, "null pointer");
+    if (V <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(fn, "non-positive size");
+    if (V > 65535) return fail(fn, "more than 65535 volumes in one launch");
+    const size_t smem = sizeof(float) * 16 * (W + 1);
+    if (smem > 48 * 1024) return fail(fn, "volume rows longer than 700 voxels are not supported");
+    dim3 grid(D * H, V);
+    unpack_grad_kernel<<<grid, kPackThreads, smem, static_cast<cudaStream_t>(stream)>>>(grad_feat_pad, grad_feat,
+                                                                                        channels_last, D, H, W);
+    return check_launch(fn);
+}

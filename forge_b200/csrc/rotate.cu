@@ -5,15 +5,20 @@
 // fetches of an output voxel are contiguous C*4-byte runs (512 B for C = 128) and the output write
 // is one contiguous run -- every HBM byte moved is an algorithmic byte.  HBM-bound.
 //
-// Work mapping: one thread per (output voxel, channel vector).  A CTA walks a compact
-// kTz x kTy x kTx block of output voxels so that the rotated input footprint stays L1/L2-hot.
+// Work mapping: a CTA owns a compact 8x8x4 block of output voxels.  Phase 1: one thread per voxel
+// evaluates the sample position once and leaves the 8 corner offsets + weights in shared memory
+// (out-of-volume corners get weight 0 and a clamped offset, so phase 2 has no predicates).
+// Phase 2: one thread per (voxel, channel vector): 4 broadcast LDS.128, 8 coalesced LDG.128,
+// 32 FFMA, 1 coalesced STG.128 -- the per-voxel scalar work is not replicated across the 32 channel
+// lanes, which is what kept v1 issue-bound at 36 % of HBM peak.
 #include "common.cuh"
 
 namespace forge {
 
 constexpr int kRotThreads = 256;
-constexpr int kTx = 8, kTy = 4, kTz = 4;            // output-voxel block per CTA
-constexpr int kTileVox = kTx * kTy * kTz;           // 128
+constexpr int kTx = 8, kTy = 8, kTz = 4;            // output-voxel block per CTA
+constexpr int kTileVox = kTx * kTy * kTz;           // 256 = one voxel per thread in phase 1
+static_assert(kTileVox == kRotThreads, "phase 1 maps one thread to one voxel");
 
 struct RotJob {
     int src, dst, kind;
@@ -31,6 +36,14 @@ __device__ __forceinline__ Tri rotate_tri(const float* __restrict__ A, float gxw
     return make_tri(unnormalize_nac(sx, W), unnormalize_nac(sy, H), unnormalize_nac(sz, D), D, H, W);
 }
 
+__device__ __forceinline__ float4 vzero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void vfma(float& a, float v, float w) { a = fmaf(v, w, a); }
+__device__ __forceinline__ void vfma(float4& a, const float4& v, float w) {
+    a.x = fmaf(v.x, w, a.x);
+    a.y = fmaf(v.y, w, a.y);
+    a.z = fmaf(v.z, w, a.z);
+    a.w = fmaf(v.w, w, a.w);
+}
 template <typename VecT>
 __device__ __forceinline__ VecT vzero();
 template <>
@@ -39,27 +52,61 @@ __device__ __forceinline__ float vzero<float>() {
 }
 template <>
 __device__ __forceinline__ float4 vzero<float4>() {
-    return make_float4(0.f, 0.f, 0.f, 0.f);
+    return vzero4();
 }
-__device__ __forceinline__ void vfma(float& a, float v, float w) { a = fmaf(v, w, a); }
-__device__ __forceinline__ void vfma(float4& a, const float4& v, float w) {
-    a.x = fmaf(v.x, w, a.x);
-    a.y = fmaf(v.y, w, a.y);
-    a.z = fmaf(v.z, w, a.z);
-    a.w = fmaf(v.w, w, a.w);
+
+struct RotTile {
+    int off[kTileVox][8];      // corner voxel offsets (clamped into the volume)
+    float w[kTileVox][8];      // corner weights, 0 for corners outside the volume
+    int out[kTileVox];         // linear output voxel index, -1 outside the volume
+    unsigned mask[kTileVox];   // in-bounds bits of the 8 corners
+    float A[12];
+};
+
+// phase 1 shared by forward and backward; optionally keeps the per-axis weights for d out/d pos
+__device__ __forceinline__ void rotate_phase1(RotTile& s, float (*frac)[6], const float* __restrict__ affine, int m,
+                                              const float* __restrict__ gx, const float* __restrict__ gy,
+                                              const float* __restrict__ gz, float inv_max, int D, int H, int W,
+                                              int tx, int ty, int tz) {
+    if (threadIdx.x < 12) s.A[threadIdx.x] = affine[12 * m + threadIdx.x];
+    __syncthreads();
+    const int v = threadIdx.x;
+    const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
+    if (w >= W || h >= H || d >= D) {
+        s.out[v] = -1;
+    } else {
+        s.out[v] = (d * H + h) * W + w;
+        const Tri t = rotate_tri(s.A, gx[w], gy[h], gz[d], inv_max, D, H, W);
+        s.mask[v] = t.mask;
+#pragma unroll
+        for (int cn = 0; cn < 8; ++cn) {
+            const bool in = (t.mask >> cn) & 1u;
+            const int x = min(max(t.x0 + (cn & 1), 0), W - 1), y = min(max(t.y0 + ((cn >> 1) & 1), 0), H - 1),
+                      z = min(max(t.z0 + (cn >> 2), 0), D - 1);
+            s.off[v][cn] = (z * H + y) * W + x;
+            s.w[v][cn] = in ? tri_weight(t, cn) : 0.f;
+        }
+        if (frac) {
+            frac[v][0] = t.wx0;
+            frac[v][1] = t.wx1;
+            frac[v][2] = t.wy0;
+            frac[v][3] = t.wy1;
+            frac[v][4] = t.wz0;
+            frac[v][5] = t.wz1;
+        }
+    }
+    __syncthreads();
 }
 
 // CU = channel vectors per voxel (C/4 for float4, C for float)
 template <typename VecT>
-__global__ void __launch_bounds__(kRotThreads)
+__global__ void __launch_bounds__(kRotThreads, 4)
 rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine, const int* __restrict__ jobs,
                   const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ gz,
                   float inv_max, VecT* __restrict__ out, int CU, int D, int H, int W, int tiles_x, int tiles_y) {
-    __shared__ float A[12];
+    __shared__ __align__(16) RotTile s;
     const int m = blockIdx.y;
     const RotJob job = {jobs[3 * m], jobs[3 * m + 1], jobs[3 * m + 2]};
-    if (threadIdx.x < 12) A[threadIdx.x] = affine[12 * m + threadIdx.x];
-    __syncthreads();
     const int tz = blockIdx.x / (tiles_x * tiles_y);
     const int trem = blockIdx.x - tz * tiles_x * tiles_y;
     const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
@@ -67,26 +114,40 @@ rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
     const VecT* src = in + static_cast<long long>(job.src) * vol * CU;
     VecT* dst = out + static_cast<long long>(job.dst) * vol * CU;
 
+    if (job.kind == 1) {   // view-0 passthrough (models/rotate.py:141)
+        for (int e = threadIdx.x; e < kTileVox * CU; e += kRotThreads) {
+            const int v = e / CU, cu = e - v * CU;
+            const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
+            if (w >= W || h >= H || d >= D) continue;
+            const long long o = (static_cast<long long>(d) * H + h) * W + w;
+            dst[o * CU + cu] = src[o * CU + cu];
+        }
+        return;
+    }
+    rotate_phase1(s, nullptr, affine, m, gx, gy, gz, inv_max, D, H, W, tx, ty, tz);
+
+#pragma unroll 2
     for (int e = threadIdx.x; e < kTileVox * CU; e += kRotThreads) {
         const int v = e / CU, cu = e - v * CU;
-        const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
-        if (w >= W || h >= H || d >= D) continue;
-        const long long o = (static_cast<long long>(d) * H + h) * W + w;
-        if (job.kind == 1) {   // view-0 passthrough (models/rotate.py:141)
-            dst[o * CU + cu] = src[o * CU + cu];
-            continue;
-        }
-        const Tri t = rotate_tri(A, gx[w], gy[h], gz[d], inv_max, D, H, W);
-        VecT acc = vzero<VecT>();
-#pragma unroll
-        for (int cn = 0; cn < 8; ++cn) {
-            if ((t.mask >> cn) & 1u) {
-                const long long vox =
-                    (static_cast<long long>(t.z0 + (cn >> 2)) * H + (t.y0 + ((cn >> 1) & 1))) * W + (t.x0 + (cn & 1));
-                vfma(acc, __ldg(src + vox * CU + cu), tri_weight(t, cn));
-            }
-        }
-        dst[o * CU + cu] = acc;
+        const int o = s.out[v];
+        if (o < 0) continue;
+        const int4 o0 = *reinterpret_cast<const int4*>(&s.off[v][0]), o1 = *reinterpret_cast<const int4*>(&s.off[v][4]);
+        const float4 w0 = *reinterpret_cast<const float4*>(&s.w[v][0]), w1 = *reinterpret_cast<const float4*>(&s.w[v][4]);
+        const VecT* p = src + cu;
+        const VecT v0 = __ldg(p + static_cast<long long>(o0.x) * CU), v1 = __ldg(p + static_cast<long long>(o0.y) * CU),
+                   v2 = __ldg(p + static_cast<long long>(o0.z) * CU), v3 = __ldg(p + static_cast<long long>(o0.w) * CU),
+                   v4 = __ldg(p + static_cast<long long>(o1.x) * CU), v5 = __ldg(p + static_cast<long long>(o1.y) * CU),
+                   v6 = __ldg(p + static_cast<long long>(o1.z) * CU), v7 = __ldg(p + static_cast<long long>(o1.w) * CU);
+        VecT acc = vzero<VecT>();      // ATen accumulation order: x fastest, then y, then z
+        vfma(acc, v0, w0.x);
+        vfma(acc, v1, w0.y);
+        vfma(acc, v2, w0.z);
+        vfma(acc, v3, w0.w);
+        vfma(acc, v4, w1.x);
+        vfma(acc, v5, w1.y);
+        vfma(acc, v6, w1.z);
+        vfma(acc, v7, w1.w);
+        dst[static_cast<long long>(o) * CU + cu] = acc;
     }
 }
 
@@ -110,12 +171,11 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
                   const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ gz,
                   float inv_max, const VecT* __restrict__ g_out, VecT* __restrict__ grad_in,
                   float* __restrict__ grad_aff, int CU, int D, int H, int W, int tiles_x, int tiles_y) {
-    __shared__ float A[12];
+    __shared__ __align__(16) RotTile s;
+    __shared__ float frac[kTileVox][6];
     __shared__ float red[12][kRotThreads / 32];
     const int m = blockIdx.y;
     const RotJob job = {jobs[3 * m], jobs[3 * m + 1], jobs[3 * m + 2]};
-    if (threadIdx.x < 12) A[threadIdx.x] = affine[12 * m + threadIdx.x];
-    __syncthreads();
     const int tz = blockIdx.x / (tiles_x * tiles_y);
     const int trem = blockIdx.x - tz * tiles_x * tiles_y;
     const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
@@ -123,7 +183,21 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
     const VecT* src = in + static_cast<long long>(job.src) * vol * CU;
     const VecT* go = g_out + static_cast<long long>(job.dst) * vol * CU;
     VecT* gin = grad_in ? grad_in + static_cast<long long>(job.src) * vol * CU : nullptr;
-    const bool need_aff = (grad_aff != nullptr) && job.kind == 0;
+
+    if (job.kind == 1) {
+        if (!gin) return;
+        for (int e = threadIdx.x; e < kTileVox * CU; e += kRotThreads) {
+            const int v = e / CU, cu = e - v * CU;
+            const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
+            if (w >= W || h >= H || d >= D) continue;
+            const long long o = (static_cast<long long>(d) * H + h) * W + w;
+            vred(gin + o * CU + cu, go[o * CU + cu]);
+        }
+        return;
+    }
+    const bool need_aff = grad_aff != nullptr;
+    rotate_phase1(s, frac, affine, m, gx, gy, gz, inv_max, D, H, W, tx, ty, tz);
+
     const float kx = 0.5f * static_cast<float>(W) * inv_max, ky = 0.5f * static_cast<float>(H) * inv_max,
                 kz = 0.5f * static_cast<float>(D) * inv_max;
     float ga[12];
@@ -132,26 +206,19 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
 
     for (int e = threadIdx.x; e < kTileVox * CU; e += kRotThreads) {
         const int v = e / CU, cu = e - v * CU;
-        const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
-        if (w >= W || h >= H || d >= D) continue;
-        const long long o = (static_cast<long long>(d) * H + h) * W + w;
-        const VecT g = go[o * CU + cu];
-        if (job.kind == 1) {
-            if (gin) vred(gin + o * CU + cu, g);
-            continue;
-        }
-        const float gxw = gx[w], gyh = gy[h], gzd = gz[d];
-        const Tri t = rotate_tri(A, gxw, gyh, gzd, inv_max, D, H, W);
+        const int o = s.out[v];
+        if (o < 0) continue;
+        const VecT g = go[static_cast<long long>(o) * CU + cu];
+        const unsigned mask = s.mask[v];
         float gix = 0.f, giy = 0.f, giz = 0.f;
 #pragma unroll
         for (int cn = 0; cn < 8; ++cn) {
-            if ((t.mask >> cn) & 1u) {
-                const long long vox =
-                    (static_cast<long long>(t.z0 + (cn >> 2)) * H + (t.y0 + ((cn >> 1) & 1))) * W + (t.x0 + (cn & 1));
-                const float wx = (cn & 1) ? t.wx1 : t.wx0, wy = (cn & 2) ? t.wy1 : t.wy0, wz = (cn & 4) ? t.wz1 : t.wz0;
-                if (gin) vred(gin + vox * CU + cu, vscale(g, wx * wy * wz));
+            if ((mask >> cn) & 1u) {     // corners outside the volume are the zero padding: no gradient
+                const long long vox = s.off[v][cn];
+                if (gin) vred(gin + vox * CU + cu, vscale(g, s.w[v][cn]));
                 if (need_aff) {
                     const float q = vdot(g, __ldg(src + vox * CU + cu));
+                    const float wx = frac[v][cn & 1], wy = frac[v][2 + ((cn >> 1) & 1)], wz = frac[v][4 + (cn >> 2)];
                     gix = fmaf((cn & 1) ? wy * wz : -(wy * wz), q, gix);
                     giy = fmaf((cn & 2) ? wx * wz : -(wx * wz), q, giy);
                     giz = fmaf((cn & 4) ? wx * wy : -(wx * wy), q, giz);
@@ -159,6 +226,8 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
             }
         }
         if (need_aff) {
+            const int w_ = tx * kTx + (v % kTx), h_ = ty * kTy + ((v / kTx) % kTy), d_ = tz * kTz + v / (kTx * kTy);
+            const float gxw = gx[w_], gyh = gy[h_], gzd = gz[d_];
             const float rx = gix * kx, ry = giy * ky, rz = giz * kz;
             ga[0] = fmaf(rx, gxw, ga[0]);
             ga[1] = fmaf(rx, gyh, ga[1]);
@@ -174,13 +243,13 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
             ga[11] += rz;
         }
     }
-    if (grad_aff != nullptr && job.kind == 0) {     // uniform per CTA
+    if (need_aff) {     // uniform per CTA
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
         for (int e = 0; e < 12; ++e) {
             float x = ga[e];
 #pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+            for (int sft = 16; sft >= 1; sft >>= 1) x += __shfl_xor_sync(0xffffffffu, x, sft);
             if (lane == 0) red[e][warp] = x;
         }
         __syncthreads();

@@ -1,0 +1,79 @@
+"""Encoder3D -- 2-D -> 3-D lifting and the render heads, mirror of reference models/encoder.py (:8-78).
+
+ResNet-50 trunk with the strides of layer3/layer4 removed (256^2 image -> 2048 x 32 x 32), reshaped to
+a 64 x 32^3 volume, one Conv3d to 128 channels; ``features_head`` (128 -> 16 ch, x2) and
+``density_head`` (128 -> 1 ch, x2, ReLU) produce the 64^3 render volumes; ``fuse`` runs the ConvGRU.
+Same child / parameter names as the reference, so its checkpoints load with ``strict=True``.
+All of this stays PyTorch/cuDNN (SURVEY 8a rows a11-a13 are host rows).
+"""
+import warnings
+
+import torch
+import torch.nn as nn
+import torchvision
+
+from .fusion import ConvGRU_3D
+
+
+class Encoder3D(nn.Module):
+    def __init__(self, config):
+        super(Encoder3D, self).__init__()
+        self.feature_extraction = get_resnet50()
+
+        self.features_head = nn.Sequential(
+            nn.ConvTranspose3d(128, 32, 4, stride=2, padding=1),
+            nn.BatchNorm3d(32),
+            nn.LeakyReLU(inplace=True),
+            nn.Conv3d(32, 16, 3, padding=1),
+            nn.BatchNorm3d(16),
+        )
+        self.density_head = nn.Sequential(
+            nn.ConvTranspose3d(128, 32, 4, stride=2, padding=1),
+            nn.BatchNorm3d(32),
+            nn.LeakyReLU(inplace=True),
+            nn.Conv3d(32, 8, 3, padding=1),
+            nn.BatchNorm3d(8),
+            nn.LeakyReLU(inplace=True),
+            nn.Conv3d(8, 1, 3, padding=1),
+            nn.ReLU(inplace=True),
+        )
+        self.conv1 = nn.Sequential(
+            nn.Conv3d(64, 128, 3, padding=1),
+            nn.BatchNorm3d(128),
+            nn.LeakyReLU(inplace=True),
+        )
+        self.fusion_feature = ConvGRU_3D(config, n_layers=1, input_size=128, hidden_size=128)
+
+    def get_feat3D(self, img):
+        z_2d = self.feature_extraction(img)
+        B, C, H, W = z_2d.shape                       # stride-8 feature map
+        z_3d = z_2d.view(-1, 64, 32, H, W)            # the lift is a reshape: 2048 = 64 ch x 32 depth
+        return self.conv1(z_3d)
+
+    def get_density3D(self, z_3d):
+        return self.density_head(z_3d)
+
+    def get_render_features(self, x):
+        return self.features_head(x)
+
+    def fuse(self, x):
+        # x in [b,t,c,d,h,w]; hidden state initialised from the view mean (reference :59-63)
+        return self.fusion_feature(x, [self.fusion_feature.fusion_conv(x.mean(dim=1))])
+
+    def forward(self, x):
+        raise NotImplementedError
+
+
+def get_resnet50():
+    """ImageNet ResNet-50 without avgpool/fc, layer3/layer4 strides set to 1 (reference :71-78).
+    Offline (no weight download possible) the trunk is randomly initialised, with a warning."""
+    try:
+        model = torchvision.models.resnet50(weights=torchvision.models.ResNet50_Weights.IMAGENET1K_V1)
+    except Exception as e:   # no network / no cached weights
+        warnings.warn("ImageNet weights for ResNet-50 unavailable (%s); using random init" % type(e).__name__)
+        model = torchvision.models.resnet50(weights=None)
+    feature = nn.Sequential(*list(model.children())[:-2])
+    for stage in (6, 7):
+        feature[stage][0].conv2.stride = (1, 1)
+        feature[stage][0].downsample[0].stride = (1, 1)
+    return feature

@@ -1,0 +1,148 @@
+"""FORGE -- joint model graph, mirror of reference models/model.py (:18-168).
+
+Same constructor / ``forward(sample, dataset, device)`` signature, return tuples and child names
+(``encoder_3d, render, rotate, encoder_traj, encoder_traj_2d, pose_head``).  What changes underneath:
+
+  * ``rotate`` + ``chose_selected`` (reference :128-129) are one K2 launch (``order=``);
+  * the per-view ``repeat`` of the fused volumes (reference :138-139) is replaced by V distinct
+    volumes + ``view2vol`` handed to K1 (the omniobject3d density clamp is applied once per volume);
+  * camera algebra stays differentiable torch on [b,t,4,4] tensors.
+
+The pose networks (``models/pose_estimator_{2d,3d}.py``) are outside the render/rotate path and are
+not re-implemented here: pass their classes (``pose_estimator_3d_cls`` / ``pose_estimator_2d_cls``,
+e.g. the reference's own) to run with predicted poses.  With ``config.train.use_gt_pose = True`` the
+reference's ``FORGE.forward`` hits an undefined ``idxs`` (reference :129); here the view order is
+computed from the ground-truth poses instead.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .encoder import Encoder3D
+from .volume_render import VolRender, origin_projection
+from .rotate import Rotate_world
+
+
+def sequence_from_distance(trans):
+    """translations [b,t,3] -> view indices sorted by squared distance to view 0 (reference :152-158)"""
+    dist = ((trans - trans[:, 0:1, :]) ** 2).sum(dim=-1)
+    _, idxs = torch.sort(dist, descending=False)
+    return idxs
+
+
+def chose_selected(tensor, idxs):
+    """tensor [b,t,...], idxs [b,t] -> per-object gather along t (reference :161-168)"""
+    assert tensor.shape[0] == len(idxs)
+    return torch.stack([tensor[i][idxs[i]] for i in range(len(idxs))])
+
+
+def _mat2quat(T):
+    """[n,4,4] -> [n,7] (w,x,y,z quaternion + translation); stand-in for reference utils/geo_utils.mat2quat
+    used only to return the ground-truth pose alongside the prediction."""
+    R, t = T[:, :3, :3], T[:, :3, 3]
+    w = torch.sqrt(torch.clamp(1 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2], min=1e-12)) / 2
+    x = (R[:, 2, 1] - R[:, 1, 2]) / (4 * w)
+    y = (R[:, 0, 2] - R[:, 2, 0]) / (4 * w)
+    z = (R[:, 1, 0] - R[:, 0, 1]) / (4 * w)
+    return torch.cat([torch.stack([w, x, y, z], dim=1), t], dim=1)
+
+
+class FORGE(nn.Module):
+    def __init__(self, config, pose_estimator_3d_cls=None, pose_estimator_2d_cls=None, mat2quat=None):
+        super(FORGE, self).__init__()
+        self.config = config
+        self.encoder_3d = Encoder3D(config)
+        self.render = VolRender(config)
+        self.rotate = Rotate_world(config)
+        self._mat2quat = mat2quat or _mat2quat
+        if pose_estimator_3d_cls is not None:
+            self.encoder_traj = pose_estimator_3d_cls(config)
+        if pose_estimator_2d_cls is not None:
+            self.encoder_traj_2d = pose_estimator_2d_cls()
+        if pose_estimator_3d_cls is not None and pose_estimator_2d_cls is not None:
+            self.pose_head = nn.Sequential(*[
+                nn.Dropout(p=0.5),
+                nn.Linear(2048, 512),
+                nn.LayerNorm(512),
+                nn.LeakyReLU(),
+                nn.Linear(512, self.encoder_traj.pose_dim + 1)
+            ])
+
+    # ---- pieces of forward, usable on their own (the eval scripts call sub-modules directly) ----
+    def lift(self, clips):
+        """[b,t,3,h,w] images -> [b,t,128,D,D,D] per-view feature volumes"""
+        b, t, c, h, w = clips.shape
+        f = self.encoder_3d.get_feat3D(clips.reshape(b * t, c, h, w))
+        return f.reshape(b, t, *f.shape[1:])
+
+    def predict_poses(self, features_raw, clips, sample, dataset, device):
+        """reference :60-87 (needs the pose networks)"""
+        if not hasattr(self, 'pose_head'):
+            raise RuntimeError("FORGE was built without pose estimators; pass pose_estimator_3d_cls / "
+                               "pose_estimator_2d_cls or set config.train.use_gt_pose = True")
+        b, t = clips.shape[:2]
+        pose_feat_3d = self.encoder_traj(features_raw, return_features=True)
+        pose_feat_2d = self.encoder_traj_2d(clips, return_features=True)
+        pred = self.pose_head(torch.cat([pose_feat_3d, pose_feat_2d], dim=-1))
+        poses_cam, conf = pred.split([self.encoder_traj.pose_dim, 1], dim=-1)
+        poses_cam = torch.cat([F.normalize(poses_cam[:, :4]), poses_cam[:, 4:]], dim=1)
+        camPoseRel_cv2 = self.encoder_traj.toSE3(poses_cam)                      # [b*(t-1),4,4]
+        canonical_pose = dataset.get_canonical_pose_cv2(device=device)
+        canonical_ext = dataset.get_canonical_extrinsics_cv2(device=device)
+        camPoses = canonical_pose.unsqueeze(0) @ camPoseRel_cv2
+        camE = torch.inverse(camPoses).reshape(b, t - 1, 4, 4)
+        camPoses = camPoses.reshape(b, t - 1, 4, 4)
+        camPoses = torch.cat([canonical_pose.reshape(1, 1, 4, 4).repeat(b, 1, 1, 1), camPoses], dim=1)
+        camE = torch.cat([canonical_ext.reshape(1, 1, 4, 4).repeat(b, 1, 1, 1), camE], dim=1)
+        gt = self._mat2quat(sample['cam_poses_rel_cv2'][:, 1:5].to(device).reshape(b * (t - 1), 4, 4))
+        return camE, camPoses, {'gt': gt, 'pred': poses_cam, 'conf': conf}
+
+    def reconstruct(self, features_raw, camPoses_cv2, idxs):
+        """per-view volumes + poses -> fused render volumes (features [b,16,2D..], densities [b,1,2D..])"""
+        D = features_raw.shape[3]
+        features_transformed = self.rotate(voxels=features_raw, camPoses_cv2=camPoses_cv2, grid_size=D, order=idxs)
+        features_mv = self.encoder_3d.fuse(features_transformed)
+        densities_mv = self.encoder_3d.get_density3D(features_mv)
+        features_mv = self.encoder_3d.get_render_features(features_mv)
+        if self.config.dataset.name == 'omniobject3d':
+            densities_mv = densities_mv.clamp(min=0.0, max=1.0)
+        return features_mv, densities_mv
+
+    def forward(self, sample, dataset, device):
+        b, t_all = sample['images'].shape[:2]
+        clips = sample['images'][:, :5].to(device)
+        t = clips.shape[1]
+        features_raw = self.lift(clips)                                           # [b,t,C,D,H,W]
+
+        if not self.config.train.use_gt_pose:
+            camE_cv2, camPoses_cv2, camPose_return = self.predict_poses(features_raw, clips, sample, dataset, device)
+        else:
+            key = '_canonicalized' if self.config.train.canonicalize else ''
+            camE_cv2 = sample['cam_extrinsics_cv2' + key].to(device)[:, :t]
+            camPoses_cv2 = sample['cam_poses_cv2' + key].to(device)[:, :t]
+            camPose_return = None
+        idxs = sequence_from_distance(camPoses_cv2[:, :, :3, 3])
+
+        if self.config.train.parameter in ('pose', 'pose_head'):
+            # pose-only training: return the pose prediction and the projected origin (reference :98-114)
+            K = sample['K_cv2'].to(device)[:, :5].reshape(b * t, 3, 3).clone()
+            K /= 2.0
+            K[:, -1, -1] = 1.0
+            origin_proj = origin_projection(camE_cv2.reshape(b * t, 4, 4)[:, :3, 3], K)
+            return camPose_return, 2 * origin_proj / self.config.dataset.img_size
+
+        # cameras of every rendered view: the (predicted) input views + the ground-truth novel views
+        camE_all = torch.cat([camE_cv2, sample['cam_extrinsics_cv2_canonicalized'][:, 5:].to(device)], dim=1)
+        camK = sample['K_cv2'].to(device)
+        cameras = {
+            'R': camE_all.reshape(b * t_all, 4, 4)[:, :3, :3],
+            'T': camE_all.reshape(b * t_all, 4, 4)[:, :3, 3],
+            'K': camK.reshape(b * t_all, 3, 3),
+        }
+        features_mv, densities_mv = self.reconstruct(features_raw, camPoses_cv2, idxs)
+        view2vol = torch.arange(b, device=device).repeat_interleave(t_all).int()
+        rendered_imgs, rendered_masks, origin_proj = self.render(cameras, features_mv, densities_mv,
+                                                                 return_origin_proj=True, view2vol=view2vol)
+        if self.config.train.use_gt_pose:
+            return rendered_imgs, rendered_masks
+        return rendered_imgs, rendered_masks, 2 * origin_proj / self.config.dataset.img_size, camPose_return

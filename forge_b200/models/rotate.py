@@ -34,6 +34,8 @@ class Rotate_world(nn.Module):
         # world location of voxel centres along one axis (the reference keeps the full [D,H,W,3] grid;
         # it is separable) and its max = volume half size, 0.4844 for 32 (ref :22-35)
         self._axis = {}
+        self._dev_axes = {}
+        self._job_cache = {}
         self.grid_coord_max = self._compute_axis(32)[1]
         self.grid_coord_max_16 = self._compute_axis(16)[1]
         self.grid_coord_max_64 = self._compute_axis(64)[1]
@@ -59,6 +61,28 @@ class Rotate_world(nn.Module):
             g = torch.linspace(-1.0, 1.0, n, dtype=torch.float32) * scale
             self._axis[n] = (g, g.max().item())
         return self._axis[n]
+
+    def _device_axes(self, D, H, W, device):
+        key = (D, H, W, str(device))
+        if key not in self._dev_axes:
+            gx, gmax = self._compute_axis(W)
+            self._dev_axes[key] = (gx.to(device), self._compute_axis(H)[0].to(device),
+                                   self._compute_axis(D)[0].to(device), gmax)
+        return self._dev_axes[key]
+
+    def _jobs(self, B, t, device, order):
+        """(src, dst, kind) per view: view 0 of each object is a copy (reference :141), the rest resample."""
+        key = (B, t, str(device))
+        if key not in self._job_cache:
+            src = torch.arange(B * t, dtype=torch.int32)
+            kind = (src % t == 0).int()
+            self._job_cache[key] = (src.to(device), kind.to(device), torch.stack([src, src, kind], dim=1).to(device))
+        src, kind, plain = self._job_cache[key]
+        if order is None:
+            return plain
+        inv = torch.argsort(order.to(device), dim=1)                         # view v lands in slot inv[b,v]
+        dst = (inv + torch.arange(B, device=device).view(B, 1) * t).reshape(-1).int()
+        return torch.stack([src, dst, kind], dim=1).contiguous()
 
     @property
     def grid_coord(self):
@@ -88,24 +112,17 @@ class Rotate_world(nn.Module):
             raise RuntimeError("forge_b200.Rotate_world needs CUDA voxels; there is no CPU path")
         B, t, C, D, H, W = voxels.shape
         device = voxels.device
-        gx, gmax = self._compute_axis(W)
-        gy, gz = self._compute_axis(H)[0], self._compute_axis(D)[0]
+        gx, gy, gz, gmax = self._device_axes(D, H, W, device)
         if grid_size != D:
             gmax = self._compute_axis(grid_size)[1]
 
         T = self.get_transformation(camPoses_cv2.to(device))                 # [B*(t-1),4,4]
-        eye = torch.eye(4, dtype=T.dtype, device=device).expand(B, 1, 4, 4)
-        A = torch.cat([eye, T.reshape(B, t - 1, 4, 4)], dim=1)[:, :, :3, :].reshape(B * t, 12)
-
-        src = torch.arange(B * t, dtype=torch.int32, device=device)
-        if order is None:
-            dst = src
-        else:
-            inv = torch.argsort(order.to(device), dim=1)                     # view v lands in slot inv[b,v]
-            dst = (inv + torch.arange(B, device=device).view(B, 1) * t).reshape(-1).int()
-        kind = (src % t == 0).int()
-        jobs = torch.stack([src, dst, kind], dim=1).contiguous()
+        A = T.new_zeros(B, t, 3, 4)
+        A[:, 0, 0, 0] = A[:, 0, 1, 1] = A[:, 0, 2, 2] = 1.0                  # view 0: identity (unused, copy job)
+        A[:, 1:] = T.reshape(B, t - 1, 4, 4)[:, :, :3, :]
+        A = A.reshape(B * t, 12)
+        jobs = self._jobs(B, t, device, order)
 
         vox_cl = ops.to_channels_last(voxels.reshape(B * t, C, D, H, W))
-        out_cl = ops.rotate_resample(vox_cl, A.float(), jobs, gx.to(device), gy.to(device), gz.to(device), gmax, B * t)
+        out_cl = ops.rotate_resample(vox_cl, A.float(), jobs, gx, gy, gz, gmax, B * t)
         return out_cl.view(B, t, D, H, W, C).permute(0, 1, 5, 2, 3, 4)

@@ -111,11 +111,10 @@ class VolRender(nn.Module):
         else:
             view2vol = view2vol.to(device=device, dtype=torch.int32)
         _, C, D, H, W = feature_3d.shape
-        feat_cl = ops.to_channels_last(feature_3d)
-        dens = density_3d.reshape(density_3d.shape[0], D, H, W)
         cam12 = camera_to_cam12(R.float(), T.float(), K.float(), (D, H, W), self.volume_physical_size)
         S = self.img_size // 2
-        feat, sil, depth = ops.raymarch(feat_cl, dens, cam12, view2vol, self._depths(device), S, S, render_depth)
+        feat, sil, depth = ops.raymarch(feature_3d, density_3d, cam12, view2vol, self._depths(device), S, S,
+                                        render_depth)
         return feat, sil, depth, R, T, K
 
     def forward(self, camera_params, feature_3d, density_3d, render_depth=False, return_origin_proj=False,

@@ -84,21 +84,52 @@ def sample_points(pts, D, H, W, align_corners):
 
 
 # ---- K1 ---------------------------------------------------------------------------------------
+def _feat_layout(feat):
+    """feat [V,16,D,H,W] (any strides) -> (tensor to hand to the library, channels_last flag)."""
+    if feat.dtype == torch.float32 and feat.permute(0, 2, 3, 4, 1).is_contiguous():
+        return feat, 1                      # channels-last in memory already (e.g. channels_last_3d convs)
+    return _f32c(feat), 0
+
+
+def pack_volume(feat, dens):
+    """feat [V,16,D,H,W], dens [V,1,D,H,W] or [V,D,H,W] -> (feat_pad [V,D+2,H+2,W+2,16], dens_quad [V,D+2,H+1,W+1,4]),
+    the zero-bordered channels-last / density-quad layouts the raymarcher reads (one pass over the data)."""
+    _require_cuda(feat, dens)
+    V, C, D, H, W = feat.shape
+    if C != 16:
+        raise ValueError("the render feature volume must have 16 channels (got %d)" % C)
+    if dens.numel() != V * D * H * W:
+        raise ValueError("density volume %s does not match feature volume %s" % (tuple(dens.shape), tuple(feat.shape)))
+    f, cl = _feat_layout(feat)
+    d = _f32c(dens)
+    feat_pad = torch.empty(V, D + 2, H + 2, W + 2, 16, dtype=torch.float32, device=feat.device)
+    dens_quad = torch.empty(V, D + 2, H + 1, W + 1, 4, dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _lib.call("forge_pack_volume", _ptr(f), cl, _ptr(d), _ptr(feat_pad), _ptr(dens_quad), V, D, H, W, _stream(feat))
+    return feat_pad, dens_quad
+
+
 class _Raymarch(torch.autograd.Function):
+    """(feat [V,16,D,H,W], dens [V,1,D,H,W], cam12 [N,12]) -> feature image, silhouette, depth."""
+
     @staticmethod
-    def forward(ctx, feat_cl, dens, cam12, view2vol, zs, S_h, S_w, render_depth):
+    def forward(ctx, feat, dens, cam12, view2vol, zs, S_h, S_w, render_depth):
         N = cam12.shape[0]
-        V, D, H, W, C = feat_cl.shape
-        dev = feat_cl.device
+        V, C, D, H, W = feat.shape
+        dev = feat.device
+        feat_pad, dens_quad = pack_volume(feat, dens)
         out = torch.empty(N, S_h, S_w, C, dtype=torch.float32, device=dev)
         sil = torch.empty(N, S_h, S_w, dtype=torch.float32, device=dev)
         depth = torch.empty(N, S_h, S_w, dtype=torch.float32, device=dev) if render_depth else None
         with torch.cuda.device(dev):
-            _lib.call("forge_raymarch_fwd", _ptr(feat_cl), _ptr(dens), _ptr(view2vol), _ptr(cam12), _ptr(zs),
-                      _ptr(out), _ptr(sil), _ptr(depth), N, V, D, H, W, S_h, S_w, zs.numel(), _stream(feat_cl))
-        ctx.save_for_backward(feat_cl, dens, cam12, view2vol, zs)
+            _lib.call("forge_raymarch_fwd", _ptr(feat_pad), _ptr(dens_quad), _ptr(view2vol), _ptr(cam12), _ptr(zs),
+                      _ptr(out), _ptr(sil), _ptr(depth), N, V, D, H, W, S_h, S_w, zs.numel(), _stream(feat))
+        if any(ctx.needs_input_grad[:3]):
+            ctx.save_for_backward(feat_pad, _f32c(dens), cam12, view2vol, zs)
         ctx.dims = (N, V, D, H, W, S_h, S_w)
         ctx.render_depth = render_depth
+        ctx.feat_cl = _feat_layout(feat)[1]
+        ctx.feat_shape, ctx.dens_shape = feat.shape, dens.shape
         if render_depth:
             return out, sil, depth
         dummy = torch.empty(0, device=dev)
@@ -107,35 +138,46 @@ class _Raymarch(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, g_sil, g_depth):
-        feat_cl, dens, cam12, view2vol, zs = ctx.saved_tensors
+        feat_pad, dens, cam12, view2vol, zs = ctx.saved_tensors
         N, V, D, H, W, S_h, S_w = ctx.dims
-        dev = feat_cl.device
+        dev = feat_pad.device
         need_f, need_d, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        g_out = torch.zeros(N, S_h, S_w, feat_cl.shape[-1], device=dev) if g_out is None else _f32c(g_out)
+        g_out = torch.zeros(N, S_h, S_w, 16, device=dev) if g_out is None else _f32c(g_out)
         g_sil = torch.zeros(N, S_h, S_w, device=dev) if g_sil is None else _f32c(g_sil)
         g_depth = _f32c(g_depth) if (ctx.render_depth and g_depth is not None) else None
-        gf = torch.zeros_like(feat_cl) if need_f else None
-        gd = torch.zeros_like(dens) if need_d else None
+        gfp = torch.zeros_like(feat_pad) if need_f else None
+        gd = torch.zeros(ctx.dens_shape, dtype=torch.float32, device=dev) if need_d else None
         gc = torch.zeros_like(cam12) if need_c else None
+        gf = None
         if need_f or need_d or need_c:
             with torch.cuda.device(dev):
-                _lib.call("forge_raymarch_bwd", _ptr(feat_cl), _ptr(dens), _ptr(view2vol), _ptr(cam12), _ptr(zs),
-                          _ptr(g_out), _ptr(g_sil), _ptr(g_depth), _ptr(gf), _ptr(gd), _ptr(gc),
-                          N, V, D, H, W, S_h, S_w, zs.numel(), _stream(feat_cl))
+                _lib.call("forge_raymarch_bwd", _ptr(feat_pad), _ptr(dens), _ptr(view2vol), _ptr(cam12), _ptr(zs),
+                          _ptr(g_out), _ptr(g_sil), _ptr(g_depth), _ptr(gfp), _ptr(gd), _ptr(gc),
+                          N, V, D, H, W, S_h, S_w, zs.numel(), _stream(feat_pad))
+                if need_f:
+                    if ctx.feat_cl:
+                        gf_cl = torch.empty(V, D, H, W, 16, dtype=torch.float32, device=dev)
+                        _lib.call("forge_unpack_volume_grad", _ptr(gfp), _ptr(gf_cl), 1, V, D, H, W, _stream(feat_pad))
+                        gf = gf_cl.permute(0, 4, 1, 2, 3)
+                    else:
+                        gf = torch.empty(ctx.feat_shape, dtype=torch.float32, device=dev)
+                        _lib.call("forge_unpack_volume_grad", _ptr(gfp), _ptr(gf), 0, V, D, H, W, _stream(feat_pad))
         return gf, gd, gc, None, None, None, None, None
 
 
-def raymarch(feat_cl, dens, cam12, view2vol, zs, S_h, S_w, render_depth=False):
-    """feat_cl [V,D,H,W,16], dens [V,D,H,W], cam12 [N,12], view2vol int32 [N], zs [P]
-    -> feat image [N,S_h,S_w,16], silhouette [N,S_h,S_w], depth [N,S_h,S_w] or None."""
-    _require_cuda(feat_cl, dens, cam12, view2vol, zs)
-    if feat_cl.shape[-1] != 16:
-        raise ValueError("the render feature volume must have 16 channels (got %d)" % feat_cl.shape[-1])
-    if dens.shape != feat_cl.shape[:-1]:
-        raise ValueError("density volume %s does not match feature volume %s" % (tuple(dens.shape), tuple(feat_cl.shape)))
+def raymarch(feat, dens, cam12, view2vol, zs, S_h, S_w, render_depth=False):
+    """feat [V,16,D,H,W] (NCDHW or channels-last strides), dens [V,1,D,H,W], cam12 [N,12], view2vol int32 [N],
+    zs [P] -> feat image [N,S_h,S_w,16], silhouette [N,S_h,S_w], depth [N,S_h,S_w] or None."""
+    _require_cuda(feat, dens, cam12, view2vol, zs)
+    if feat.dim() != 5 or feat.shape[1] != 16:
+        raise ValueError("the render feature volume must be [V,16,D,H,W] (got %s)" % (tuple(feat.shape),))
+    if dens.numel() != feat.numel() // 16:
+        raise ValueError("density volume %s does not match feature volume %s" % (tuple(dens.shape), tuple(feat.shape)))
     if cam12.shape[0] != view2vol.numel():
         raise ValueError("cam12 and view2vol disagree on the number of views")
-    out, sil, depth = _Raymarch.apply(_f32c(feat_cl), _f32c(dens), _f32c(cam12), view2vol.int().contiguous(),
+    if feat.dtype != torch.float32:
+        feat = feat.float()
+    out, sil, depth = _Raymarch.apply(feat, dens.float(), _f32c(cam12), view2vol.int().contiguous(),
                                       _f32c(zs), int(S_h), int(S_w), bool(render_depth))
     return out, sil, (depth if render_depth else None)
 

@@ -92,3 +92,35 @@ def rotate_inputs(n_objects, n_views, channels, grid, seed=0, device='cpu'):
     vox = torch.randn(n_objects, n_views, channels, grid, grid, grid, generator=g)
     poses = torch.stack([ring_cameras(n_views, seed=seed * 1000 + b)[2] for b in range(n_objects)])
     return vox.to(device), poses.to(device)
+
+
+def kubric_batch(n_objects, n_views_all=10, img_size=256, camera_z=1.5, seed=0):
+    """A batch dict of the shape reference dataset/kubric.py:390-402 produces (random images, ring cameras
+    canonicalised so that view 0 has extrinsics [I | (0,0,camera_z)])."""
+    g = torch.Generator().manual_seed(seed)
+    E, P = [], []
+    for b in range(n_objects):
+        R, T, pose = ring_cameras(n_views_all, camera_z=camera_z, seed=seed * 1000 + b)
+        e = torch.eye(4).repeat(n_views_all, 1, 1)
+        e[:, :3, :3], e[:, :3, 3] = R, T
+        E.append(e)
+        P.append(pose)
+    E, P = torch.stack(E), torch.stack(P)
+    rel = torch.linalg.inv(P[:, :1]) @ P                      # pose of view i in view 0's frame
+    every2 = torch.linalg.inv(P[:, :-1]) @ P[:, 1:]
+    return {
+        'images': torch.rand(n_objects, n_views_all, 3, img_size, img_size, generator=g),
+        'fg_probabilities': (torch.rand(n_objects, n_views_all, 1, img_size, img_size, generator=g) > 0.5).float(),
+        'K_cv2': intrinsics(n_objects * n_views_all, img_size).reshape(n_objects, n_views_all, 3, 3),
+        'cam_extrinsics_cv2': E.clone(), 'cam_poses_cv2': P.clone(),
+        'cam_extrinsics_cv2_canonicalized': E, 'cam_poses_cv2_canonicalized': P,
+        'cam_poses_rel_cv2': rel, 'cam_poses_rel_every2_cv2': every2,
+        'seq_name': ['synthetic_%d' % b for b in range(n_objects)],
+    }
+
+
+def shard_objects(n_objects, rank, world_size):
+    """Contiguous shard [lo, hi) of independent objects for one rank (objects never interact)."""
+    base, rem = divmod(n_objects, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

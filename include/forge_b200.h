@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 3
+#define FORGE_ABI_VERSION 4
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -34,6 +34,20 @@ const char* forge_last_error(void);
 int forge_ncs_to_nsc(const float* src, float* dst, int n, int C, long long S, void* stream);
 int forge_nsc_to_ncs(const float* src, float* dst, int n, int C, long long S, void* stream);
 
+/* ---- render-volume packing ------------------------------------------------------------------
+ * Builds the two device layouts K1 reads, once per DISTINCT volume (the reference materialises one
+ * copy per rendered view, models/model.py:138-139, and ATen's sampler then gathers 17 channels that
+ * lie 1 MiB apart):
+ *   feat_pad  [V][D+2][H+2][W+2][16]  channels-last, one-voxel zero border (= zeros padding)
+ *   dens_quad [V][D+2][H+1][W+1][4]   (d(z,y,x), d(z,y,x+1), d(z,y+1,x), d(z,y+1,x+1)); index
+ *                                     (z+1, y+1, x+1) for z in [-1,D], y in [-1,H-1], x in [-1,W-1]
+ * feat is [V][16][D][H][W] (feat_channels_last = 0) or [V][D][H][W][16] (= 1); dens is [V][D][H][W].
+ * forge_unpack_volume_grad maps a gradient in feat_pad layout back to feat's layout. */
+int forge_pack_volume(const float* feat, int feat_channels_last, const float* dens, float* feat_pad,
+                      float* dens_quad, int V, int D, int H, int W, void* stream);
+int forge_unpack_volume_grad(const float* grad_feat_pad, float* grad_feat, int channels_last, int V,
+                             int D, int H, int W, void* stream);
+
 /* ---- K1: fused volume raymarcher ----------------------------------------------------------
  * Replaces models/volume_render.py:53-63 = PyTorch3D cameras_from_opencv_projection +
  * NDCGridRaysampler + VolumeSampler (2x grid_sample, align_corners=True, zeros padding) +
@@ -44,21 +58,23 @@ int forge_nsc_to_ncs(const float* src, float* dst, int n, int C, long long S, vo
  *   compositing    T_0 = 1; w_k = s_k T_k; T_{k+1} = T_k (1 - s_k);
  *                  feat = sum w_k f_k; sil = 1 - T_P; depth = sum w_k zs[k]
  *
- *   feat_cl  [V][D][H][W][16]   dens [V][D][H][W]   view2vol [N] (volume index of each view)
+ *   feat_pad, dens_quad: see forge_pack_volume;  view2vol [N] (volume index of each view)
  *   out_feat [N][S_h][S_w][16]  out_sil [N][S_h][S_w]  out_depth [N][S_h][S_w] or NULL
  */
-int forge_raymarch_fwd(const float* feat_cl, const float* dens, const int* view2vol, const float* cam12,
-                       const float* zs, float* out_feat, float* out_sil, float* out_depth,
-                       int N, int V, int D, int H, int W, int S_h, int S_w, int P, void* stream);
+int forge_raymarch_fwd(const float* feat_pad, const float* dens_quad, const int* view2vol,
+                       const float* cam12, const float* zs, float* out_feat, float* out_sil,
+                       float* out_depth, int N, int V, int D, int H, int W, int S_h, int S_w, int P,
+                       void* stream);
 
-/* Backward of forge_raymarch_fwd.  g_* are the upstream gradients (g_depth may be NULL).
- * grad_feat_cl [V][D][H][W][16] and grad_dens [V][D][H][W] are ACCUMULATED into (caller zeroes
- * them); either may be NULL to skip that gradient (pose-only refinement, reference
- * kubric_eval.py:450-504).  grad_cam12 [N][12] is accumulated into (caller zeroes), may be NULL.
- * Replaces the autograd graph PyTorch builds through the sequence named above. */
-int forge_raymarch_bwd(const float* feat_cl, const float* dens, const int* view2vol, const float* cam12,
+/* Backward of forge_raymarch_fwd.  g_* are the upstream gradients (g_depth may be NULL).  Reads the
+ * padded features and the PLAIN density volume dens [V][D][H][W].  grad_feat_pad (feat_pad layout)
+ * and grad_dens [V][D][H][W] are ACCUMULATED into (caller zeroes them); either may be NULL to skip
+ * that gradient (pose-only refinement, reference kubric_eval.py:450-504).  grad_cam12 [N][12] is
+ * accumulated into (caller zeroes), may be NULL.  Replaces the autograd graph PyTorch builds
+ * through the sequence named above. */
+int forge_raymarch_bwd(const float* feat_pad, const float* dens, const int* view2vol, const float* cam12,
                        const float* zs, const float* g_feat, const float* g_sil, const float* g_depth,
-                       float* grad_feat_cl, float* grad_dens, float* grad_cam12,
+                       float* grad_feat_pad, float* grad_dens, float* grad_cam12,
                        int N, int V, int D, int H, int W, int S_h, int S_w, int P, void* stream);
 
 /* ---- K2: affine feature-volume resample ---------------------------------------------------

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     path = build.build()
     lib = ctypes.CDLL(path)
     names = _declared_symbols()
-    assert len(names) >= 9
+    assert len(names) >= 11
     for name in names:
         assert hasattr(lib, name), "libforge_b200.so does not export %s" % name
     assert set(names) == set(_lib._SIGNATURES), "ctypes binding and header disagree"
@@ -42,8 +42,8 @@ def test_product_path_refuses_cpu_tensors():
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.to_channels_last(torch.zeros(1, 4, 2, 2, 2))
     with pytest.raises(RuntimeError, match="CUDA"):
-        ops.raymarch(torch.zeros(1, 2, 2, 2, 16), torch.zeros(1, 2, 2, 2), torch.zeros(1, 12), torch.zeros(1).int(),
-                     torch.zeros(4), 2, 2)
+        ops.raymarch(torch.zeros(1, 16, 2, 2, 2), torch.zeros(1, 1, 2, 2, 2), torch.zeros(1, 12),
+                     torch.zeros(1).int(), torch.zeros(4), 2, 2)
 
 
 def test_product_never_imports_oracle():

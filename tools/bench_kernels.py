@@ -83,16 +83,25 @@ def main():
     Kh[:, 2, 2] = 1
     cam12 = camera_to_cam12(inp['R'], inp['T'], Kh, (D, D, D), 1.0).contiguous()
     zs = m._depths(DEV)
-    dens4 = inp['dens'].reshape(b, D, D, D)
-    feat_cl = ops.to_channels_last(inp['feat'])
+    from forge_b200 import _lib
+    fp, dq = ops.pack_volume(inp['feat'], inp['dens'])
+    o_feat = torch.empty(N, S, S, 16, device=DEV)
+    o_sil = torch.empty(N, S, S, device=DEV)
+    o_dep = torch.empty(N, S, S, device=DEV)
+
+    def k1():
+        _lib.call("forge_raymarch_fwd", fp.data_ptr(), dq.data_ptr(), inp['view2vol'].data_ptr(), cam12.data_ptr(),
+                  zs.data_ptr(), o_feat.data_ptr(), o_sil.data_ptr(), o_dep.data_ptr(), N, b, D, D, D, S, S, P,
+                  torch.cuda.current_stream().cuda_stream)
 
     with torch.no_grad():
         if want("relayout"):
-            ms, best = timeit(lambda: ops.to_channels_last(inp['feat']), args.reps, flush)
-            report("ncs_to_nsc (feat %dx16x%d^3)" % (b, D), ms, best, 2 * inp['feat'].numel() * 4)
+            ms, best = timeit(lambda: ops.pack_volume(inp['feat'], inp['dens']), args.reps, flush)
+            report("pack_volume (%dx17x%d^3 NCDHW -> padded NDHWC + quads)" % (b, D), ms, best,
+                   (inp['feat'].numel() + inp['dens'].numel()) * 4 + (fp.numel() + dq.numel()) * 4)
         if want("k1"):
             k1_bytes = b * 17 * D ** 3 * 4 + rays * 18 * 4 + N * 48
-            ms, best = timeit(lambda: ops.raymarch(feat_cl, dens4, cam12, inp['view2vol'], zs, S, S, True), args.reps, flush)
+            ms, best = timeit(k1, args.reps, flush)
             report("raymarch_fwd", ms, best, k1_bytes, Mrays_per_s=round(rays / ms / 1e3, 1),
                    fp32_TFLOPs=round(rays * P * 366 / ms / 1e9, 2))
         if want("volrender"):
@@ -107,10 +116,25 @@ def main():
             rot = Rotate_world(cfg).to(DEV)
             vox_cl = vox.permute(0, 1, 3, 4, 5, 2).contiguous().permute(0, 1, 5, 2, 3, 4)
             k2_bytes = 2 * b * t * C * n ** 3 * 4
+            vcl = vox_cl.permute(0, 1, 3, 4, 5, 2).reshape(b * t, n, n, n, C)
+            assert vcl.data_ptr() == vox_cl.data_ptr()
+            gxd, gyd, gzd, gmax = rot._device_axes(n, n, n, DEV)
+            A = torch.zeros(b, t, 3, 4, device=DEV)
+            A[:, 1:] = rot.get_transformation(poses).reshape(b, t - 1, 4, 4)[:, :, :3, :]
+            A = A.reshape(b * t, 12).contiguous()
+            jobs = rot._jobs(b, t, DEV, None)
+            out_cl = torch.empty_like(vcl)
+
+            def k2():
+                _lib.call("forge_rotate_fwd", vcl.data_ptr(), A.data_ptr(), jobs.data_ptr(), gxd.data_ptr(), gyd.data_ptr(),
+                          gzd.data_ptr(), float(gmax), out_cl.data_ptr(), b * t, C, n, n, n,
+                          torch.cuda.current_stream().cuda_stream)
+            ms, best = timeit(k2, args.reps, flush)
+            report("rotate_fwd kernel (C-ABI call, %dx%dx%dx%d^3 channels-last)" % (b, t, C, n), ms, best, k2_bytes)
             ms, best = timeit(lambda: rot(vox_cl, poses, grid_size=n), args.reps, flush)
-            report("rotate_fwd channels-last in/out (%dx%dx%dx%d^3)" % (b, t, C, n), ms, best, k2_bytes)
+            report("Rotate_world.forward channels-last in/out (kernel + torch pose glue)", ms, best, k2_bytes)
             ms, best = timeit(lambda: rot(vox, poses, grid_size=n), args.reps, flush)
-            report("rotate_fwd NCDHW in (+relayout)", ms, best, k2_bytes)
+            report("Rotate_world.forward NCDHW in (+relayout kernel)", ms, best, k2_bytes)
             if args.ref:
                 from oracle import reference_path as rp
                 ms, best = timeit(lambda: rp.rotate_world_forward(vox, poses, n, 1.0), max(3, args.reps // 4), flush)
@@ -130,15 +154,15 @@ def main():
             report("REFERENCE raymarch core (PyTorch3D op sequence) on GPU", ms, best, None, Mrays_per_s=round(rays / ms / 1e3, 2))
 
     if args.bwd:
-        feat_g = feat_cl.clone().requires_grad_(True)
-        dens_g = dens4.clone().requires_grad_(True)
+        feat_g = inp['feat'].clone().requires_grad_(True)
+        dens_g = inp['dens'].clone().requires_grad_(True)
         cam_g = cam12.clone().requires_grad_(True)
         go = torch.randn(N, S, S, 16, device=DEV)
         gs = torch.randn(N, S, S, device=DEV)
 
         def fb(pose_only):
-            f = feat_cl if pose_only else feat_g
-            d = dens4 if pose_only else dens_g
+            f = inp['feat'] if pose_only else feat_g
+            d = inp['dens'] if pose_only else dens_g
             o, s, dep = ops.raymarch(f, d, cam_g, inp['view2vol'], zs, S, S, True)
             torch.autograd.backward([o, s, dep], [go, gs, gs])
         for po in (False, True):
