@@ -21,12 +21,13 @@ _SIGNATURES = {
     "forge_pack_volume": (_c.c_int, [_F, _I, _F, _F, _F, _I, _I, _I, _I, _F]),
     "forge_unpack_volume_grad": (_c.c_int, [_F, _F, _I, _I, _I, _I, _I, _F]),
     "forge_raymarch_fwd": (_c.c_int, [_F] * 8 + [_I] * 8 + [_F]),
-    "forge_raymarch_bwd": (_c.c_int, [_F] * 11 + [_I] * 8 + [_F]),
+    "forge_raymarch_bwd": (_c.c_int, [_F] * 12 + [_I] * 8 + [_F]),
+    "forge_raymarch_bwd_workspace": (_c.c_longlong, [_I] * 4),
     "forge_rotate_fwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F] + [_I] * 5 + [_F]),
     "forge_rotate_bwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F, _F, _F] + [_I] * 5 + [_F]),
     "forge_sample_points": (_c.c_int, [_F, _I, _I, _I, _I, _I, _F, _F, _F]),
 }
-ABI_VERSION = 4
+ABI_VERSION = 6
 
 _lock = threading.Lock()
 _lib = None

@@ -17,6 +17,8 @@
 // The two lanes split the density planes (dz = c) and combine with one xor-shuffle.  Samples outside
 // the exact ray/volume slab are skipped: under zeros padding they contribute exactly 0 and multiply
 // the transmittance by exactly 1.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace forge {
@@ -115,7 +117,8 @@ __device__ __forceinline__ f8 ldg256(const float* p) {
     return r;
 }
 
-__global__ void __launch_bounds__(kRmThreads, 2)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kRmThreads, kMinBlocks)
 raymarch_fwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict__ dens_quad,
                     const int* __restrict__ view2vol, const float* __restrict__ cam12, const float* __restrict__ zs_g,
                     float* __restrict__ out_feat, float* __restrict__ out_sil, float* __restrict__ out_depth, int D,
@@ -213,129 +216,134 @@ raymarch_fwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
 // d L / d p_k is accumulated per lane into d L / d o and d L / d dir and reduced once per CTA into
 // the 12 camera floats of the view.
 //
-// Mapping: 4 lanes per ray (lane c owns channels 4c..4c+3), 8x8 pixel tile per CTA.  Features come
-// from the padded volume (and grad_feat goes to a padded volume of the same shape); densities are
-// read from / scattered to the plain [V][D][H][W] layout, 2 corners per lane.
-constexpr int kRaysPerCta = kRmThreads / 4;
+// Same mapping and packed inputs as the forward kernel (2 lanes per ray, 256-bit corner loads, density
+// quads, 16x8 pixel tile per CTA).  grad_feat goes to a volume in feat_pad layout, grad_dens to a
+// zero-bordered [V][D+2][H+2][W+2] volume, so neither scatter needs bounds predicates.
+constexpr int kRaysPerCta = kRmThreads / 2;
 
-__device__ __forceinline__ Tri sample_tri(const Ray& r, float z, int D, int H, int W) {
-    const float px = __fadd_rn(r.ox, __fmul_rn(z, r.dx));
-    const float py = __fadd_rn(r.oy, __fmul_rn(z, r.dy));
-    const float pz = __fadd_rn(r.oz, __fmul_rn(z, r.dz));
-    return make_tri(unnormalize_ac(px, W), unnormalize_ac(py, H), unnormalize_ac(pz, D), D, H, W);
-}
-
-// density at the sample: lane c of the quad fetches corners (dz = c>>1, dy = c&1, dx = 0/1)
-__device__ __forceinline__ float quad_density(const Tri& t, const float* __restrict__ dens, int H, int W, int c) {
-    const int c0 = ((c >> 1) << 2) | ((c & 1) << 1);
-    const int zz = t.z0 + (c >> 1), yy = t.y0 + (c & 1);
-    const long long row = (static_cast<long long>(zz) * H + yy) * W + t.x0;
-    float part = 0.f;
-    if ((t.mask >> c0) & 1u) part = __ldg(dens + row) * tri_weight(t, c0);
-    if ((t.mask >> (c0 + 1)) & 1u) part = fmaf(__ldg(dens + row + 1), tri_weight(t, c0 + 1), part);
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    return part;
-}
-
-__global__ void __launch_bounds__(kRmThreads)
-raymarch_bwd_kernel(const float4* __restrict__ feat_pad, const float* __restrict__ dens,
+__global__ void __launch_bounds__(kRmThreads, 2)
+raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict__ dens_quad,
                     const int* __restrict__ view2vol, const float* __restrict__ cam12, const float* __restrict__ zs_g,
-                    const float4* __restrict__ g_feat, const float* __restrict__ g_sil,
+                    const float* __restrict__ g_feat, const float* __restrict__ g_sil,
                     const float* __restrict__ g_depth, float* __restrict__ grad_feat_pad,
-                    float* __restrict__ grad_dens, float* __restrict__ grad_cam, int D, int H, int W, int Sh, int Sw,
-                    int P, int tiles_x) {
-    extern __shared__ float smem[];
-    float* zs = smem;                       // [P]
-    float* cam = zs + P;                    // [12]
-    float* red = cam + 12;                  // [12][8 warps]
-    float* s_sig = red + 12 * (kRmThreads / 32);   // [P][64]
-    float* s_a = s_sig + P * kRaysPerCta;
-    float* s_T = s_a + P * kRaysPerCta;
-
+                    float* __restrict__ grad_dens_pad, float* __restrict__ grad_cam, float* __restrict__ workspace,
+                    int D, int H, int W, int Sh, int Sw, int P, int tiles_x) {
+    __shared__ float zs[kMaxP];
+    __shared__ float cam[12];
+    __shared__ float red[12 * (kRmThreads / 32)];
+    // per-CTA stash [P][3][128 rays] in the caller's workspace (L2-resident between the two passes);
+    // keeping it out of shared memory leaves the whole unified L1 to the corner gathers
+    float* stash = workspace + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * P * 3 * kRaysPerCta;
     const int n = blockIdx.y;
+
     for (int k = threadIdx.x; k < P; k += kRmThreads) zs[k] = zs_g[k];
     if (threadIdx.x < 12) cam[threadIdx.x] = cam12[n * 12 + threadIdx.x];
     __syncthreads();
 
-    const bool need_feat = grad_feat_pad != nullptr, need_dens = grad_dens != nullptr, need_cam = grad_cam != nullptr;
-    const int c = threadIdx.x & 3, ray = threadIdx.x >> 2;
-    const int warp = threadIdx.x >> 5, q = (threadIdx.x & 31) >> 2;
+    const bool need_feat = grad_feat_pad != nullptr, need_dens = grad_dens_pad != nullptr, need_cam = grad_cam != nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = lane & 1, q = lane >> 1, ray = threadIdx.x >> 1;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-    const int j = tx * 8 + (warp & 1) * 4 + (q & 3);
-    const int i = ty * 8 + (warp >> 1) * 2 + (q >> 2);
+    const int j = tx * 16 + (warp & 3) * 4 + (q & 3);
+    const int i = ty * 8 + (warp >> 2) * 4 + (q >> 2);
     const bool valid = (i < Sh) && (j < Sw);
     Ray r = make_ray(cam, i, j, zs, P, D, H, W);
     if (!valid) r.k1 = 0;
     int kw0 = r.k1 > r.k0 ? r.k0 : P, kw1 = r.k1 > r.k0 ? r.k1 : 0;
 #pragma unroll
-    for (int s = 16; s >= 4; s >>= 1) {
+    for (int s = 16; s >= 2; s >>= 1) {
         kw0 = min(kw0, __shfl_xor_sync(0xffffffffu, kw0, s));
         kw1 = max(kw1, __shfl_xor_sync(0xffffffffu, kw1, s));
     }
 
-    const int Wp = W + 2, Hp = H + 2;
-    const long long vol = static_cast<long long>(view2vol[n]);
-    const long long volp = vol * (D + 2) * Hp * Wp;
-    const float4* fv = feat_pad + volp * 4 + c;       // 4 float4 per padded voxel
-    const float* dv = dens + vol * D * H * W;
-    float* gfv = need_feat ? grad_feat_pad + volp * 16 + 4 * c : nullptr;
-    float* gdv = need_dens ? grad_dens + vol * D * H * W : nullptr;
+    const int Wp = W + 2, Hp = H + 2, Wq = W + 1, Hq = H + 1;
+    const long long v = view2vol[n];
+    const long long volp = v * (D + 2) * Hp * Wp;
+    const float* fv = feat_pad + volp * 16 + c * 8;
+    const float4* qv = dens_quad + v * (D + 2) * Hq * Wq;
+    float* gdv = need_dens ? grad_dens_pad + volp : nullptr;
+    const int row_y = Wp * 16, row_z = Hp * Wp * 16;
 
-    float4 gF = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gF[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gF[e] = 0.f;
     float gO = 0.f, gD = 0.f;
     if (valid) {
         const long long pix = (static_cast<long long>(n) * Sh + i) * Sw + j;
-        gF = g_feat[pix * 4 + c];
+        const float4* gp = reinterpret_cast<const float4*>(g_feat + pix * 16 + c * 8);
+        const float4 g0 = gp[0], g1 = gp[1];
+        gF[0] = g0.x, gF[1] = g0.y, gF[2] = g0.z, gF[3] = g0.w;
+        gF[4] = g1.x, gF[5] = g1.y, gF[6] = g1.z, gF[7] = g1.w;
         gO = g_sil[pix];
         if (g_depth) gD = g_depth[pix];
     }
     const float sx = 0.5f * static_cast<float>(W - 1), sy = 0.5f * static_cast<float>(H - 1),
                 sz = 0.5f * static_cast<float>(D - 1);
     float go0 = 0.f, go1 = 0.f, go2 = 0.f, gd0 = 0.f, gd1 = 0.f, gd2 = 0.f;   // per-lane partials
+    // scatter layout: each RED.128 instruction of a ray should fill whole 32-byte sectors, so lane c
+    // adds channels [4c, 4c+4) (first sector) and [8+4c, 8+4c+4) (second sector); half of those
+    // upstream-gradient values live in the partner lane
+    float sA[4], sB[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float mine_lo = gF[e], mine_hi = gF[4 + e];
+        const float other_lo = __shfl_xor_sync(0xffffffffu, mine_lo, 1), other_hi = __shfl_xor_sync(0xffffffffu, mine_hi, 1);
+        sA[e] = c ? other_hi : mine_lo;     // channels 4c+e of the ray:      c=0 -> own gF[e],   c=1 -> lane0's gF[4+e]
+        sB[e] = c ? mine_hi : other_lo;     // channels 8+4c+e of the ray:    c=0 -> lane1's gF[e], c=1 -> own gF[4+e]
+    }
+    float* gfs = need_feat ? grad_feat_pad + volp * 16 + c * 4 : nullptr;
 
     // ---- pass A: front to back ----
     float T = 1.f;
     for (int k = kw0; k < kw1; ++k) {
-        const bool act = (k >= r.k0) && (k < r.k1);
         const float z = zs[k];
-        Tri t = sample_tri(r, z, D, H, W);
-        if (!act) t.mask = 0;
-        const float sigma = quad_density(t, dv, H, W, c);
+        const Foot f = sample_foot(r, z, D, H, W);
+        const bool act = f.in && (k >= r.k0) && (k < r.k1);
+        const float w00 = __fmul_rn(f.wx0, f.wy0), w10 = __fmul_rn(f.wx1, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1),
+                    w11 = __fmul_rn(f.wx1, f.wy1);
+        float part = 0.f;
+        if (act) {
+            const float wz = c ? f.wz1 : f.wz0;
+            const float4 d4 = __ldg(qv + (static_cast<long long>(f.z0 + 1 + c) * Hq + (f.y0 + 1)) * Wq + (f.x0 + 1));
+            part = __fmul_rn(w00, wz) * d4.x;
+            part = fmaf(__fmul_rn(w10, wz), d4.y, part);
+            part = fmaf(__fmul_rn(w01, wz), d4.z, part);
+            part = fmaf(__fmul_rn(w11, wz), d4.w, part);
+        }
+        const float sigma = part + __shfl_xor_sync(0xffffffffu, part, 1);
         const float wk = sigma * T;
         float a_part = 0.f, gix = 0.f, giy = 0.f, giz = 0.f;
-        if (t.mask) {
+        if (act) {
             const bool scatter = need_feat && (wk != 0.f);
-            // mask != 0 => base voxel in [-1, size-1]: all 8 padded corners are addressable
-            const int base = ((t.z0 + 1) * Hp + (t.y0 + 1)) * Wp + (t.x0 + 1);
+            const int off = ((f.z0 + 1) * Hp + (f.y0 + 1)) * row_y + (f.x0 + 1) * 16;
 #pragma unroll
             for (int cn = 0; cn < 8; ++cn) {
-                if ((t.mask >> cn) & 1u) {
-                    const int vox = base + ((cn & 4) ? Hp * Wp : 0) + ((cn & 2) ? Wp : 0) + (cn & 1);
-                    const float4 val = __ldg(fv + static_cast<long long>(vox) * 4);
-                    const float q4 = fmaf(gF.x, val.x, fmaf(gF.y, val.y, fmaf(gF.z, val.z, gF.w * val.w)));
-                    const float wx = (cn & 1) ? t.wx1 : t.wx0, wy = (cn & 2) ? t.wy1 : t.wy0, wz = (cn & 4) ? t.wz1 : t.wz0;
-                    const float wyz = wy * wz;
-                    const float w = wx * wyz;
-                    a_part = fmaf(w, q4, a_part);
-                    gix = fmaf((cn & 1) ? wyz : -wyz, q4, gix);
-                    giy = fmaf((cn & 2) ? wx * wz : -(wx * wz), q4, giy);
-                    giz = fmaf((cn & 4) ? wx * wy : -(wx * wy), q4, giz);
-                    if (scatter) {
-                        const float cw = wk * w;
-                        red_add_v4(gfv + static_cast<long long>(vox) * 16,
-                                   make_float4(cw * gF.x, cw * gF.y, cw * gF.z, cw * gF.w));
-                    }
+                const int o = off + ((cn & 4) ? row_z : 0) + ((cn & 2) ? row_y : 0) + ((cn & 1) ? 16 : 0);
+                const f8 val = ldg256(fv + o);
+                float qd = gF[0] * val.v[0];
+#pragma unroll
+                for (int e = 1; e < 8; ++e) qd = fmaf(gF[e], val.v[e], qd);
+                const float wx = (cn & 1) ? f.wx1 : f.wx0, wy = (cn & 2) ? f.wy1 : f.wy0, wz = (cn & 4) ? f.wz1 : f.wz0;
+                const float wxy = (cn & 2) ? ((cn & 1) ? w11 : w01) : ((cn & 1) ? w10 : w00);
+                const float w = wxy * wz;
+                a_part = fmaf(w, qd, a_part);
+                gix = fmaf((cn & 1) ? wy * wz : -(wy * wz), qd, gix);
+                giy = fmaf((cn & 2) ? wx * wz : -(wx * wz), qd, giy);
+                giz = fmaf((cn & 4) ? wxy : -wxy, qd, giz);
+                if (scatter) {
+                    const float cw = wk * w;
+                    red_add_v4(gfs + o, make_float4(cw * sA[0], cw * sA[1], cw * sA[2], cw * sA[3]));
+                    red_add_v4(gfs + o + 8, make_float4(cw * sB[0], cw * sB[1], cw * sB[2], cw * sB[3]));
                 }
             }
         }
         a_part += __shfl_xor_sync(0xffffffffu, a_part, 1);
-        a_part += __shfl_xor_sync(0xffffffffu, a_part, 2);
         if (act) {
             if (c == 0) {
-                s_sig[k * kRaysPerCta + ray] = sigma;
-                s_a[k * kRaysPerCta + ray] = fmaf(gD, z, a_part);
-                s_T[k * kRaysPerCta + ray] = T;
+                float* st = stash + static_cast<size_t>(k) * 3 * kRaysPerCta + ray;
+                st[0] = sigma;
+                st[kRaysPerCta] = fmaf(gD, z, a_part);
+                st[2 * kRaysPerCta] = T;
             }
             const float px = wk * gix * sx, py = wk * giy * sy, pz = wk * giz * sz;
             go0 += px;
@@ -347,50 +355,51 @@ raymarch_bwd_kernel(const float4* __restrict__ feat_pad, const float* __restrict
         }
         T = T * (1.f - sigma);
     }
-    __syncwarp();
+    __syncwarp();     // lane 0's stash writes are visible to lane 1 of the pair (same warp, global memory)
 
-    // ---- pass B: back to front (per-quad loop, no shuffles inside) ----
+    // ---- pass B: back to front (per-ray loop, no shuffles inside; lane c owns density plane dz = c) ----
     if (need_dens || need_cam) {
         float Bk = -gO;
-        const int c0 = ((c >> 1) << 2) | ((c & 1) << 1);
         for (int k = r.k1 - 1; k >= r.k0; --k) {
-            const float sigma = s_sig[k * kRaysPerCta + ray], a = s_a[k * kRaysPerCta + ray], Tk = s_T[k * kRaysPerCta + ray];
+            const float z = zs[k];
+            const Foot f = sample_foot(r, z, D, H, W);
+            if (!f.in) continue;            // never stashed: sigma = 0, B unchanged
+            const float* st = stash + static_cast<size_t>(k) * 3 * kRaysPerCta + ray;
+            const float sigma = st[0], a = st[kRaysPerCta], Tk = st[2 * kRaysPerCta];
             const float dsig = Tk * (a - Bk);
             Bk = fmaf(a, sigma, (1.f - sigma) * Bk);
-            const float z = zs[k];
-            const Tri t = sample_tri(r, z, D, H, W);
-            const long long row = (static_cast<long long>(t.z0 + (c >> 1)) * H + (t.y0 + (c & 1))) * W + t.x0;
-            const float wy = (c & 1) ? t.wy1 : t.wy0, wz = (c >> 1) ? t.wz1 : t.wz0;
-            float gix = 0.f, giy = 0.f, giz = 0.f;
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                if ((t.mask >> (c0 + dx)) & 1u) {
-                    const float wx = dx ? t.wx1 : t.wx0;
-                    if (need_dens) atomicAdd(gdv + row + dx, dsig * (wx * wy * wz));
-                    if (need_cam) {
-                        const float val = __ldg(dv + row + dx);
-                        gix = fmaf(dx ? wy * wz : -(wy * wz), val, gix);
-                        giy = fmaf((c & 1) ? wx * wz : -(wx * wz), val, giy);
-                        giz = fmaf((c >> 1) ? wx * wy : -(wx * wy), val, giz);
-                    }
-                }
+            const float wz = c ? f.wz1 : f.wz0;
+            if (need_dens) {
+                float* g = gdv + (static_cast<long long>(f.z0 + 1 + c) * Hp + (f.y0 + 1)) * Wp + (f.x0 + 1);
+                const float dz = dsig * wz;
+                atomicAdd(g, dz * (f.wx0 * f.wy0));
+                atomicAdd(g + 1, dz * (f.wx1 * f.wy0));
+                atomicAdd(g + Wp, dz * (f.wx0 * f.wy1));
+                atomicAdd(g + Wp + 1, dz * (f.wx1 * f.wy1));
             }
-            const float px = dsig * gix * sx, py = dsig * giy * sy, pz = dsig * giz * sz;
-            go0 += px;
-            go1 += py;
-            go2 += pz;
-            gd0 = fmaf(z, px, gd0);
-            gd1 = fmaf(z, py, gd1);
-            gd2 = fmaf(z, pz, gd2);
+            if (need_cam) {
+                const float4 d4 = __ldg(qv + (static_cast<long long>(f.z0 + 1 + c) * Hq + (f.y0 + 1)) * Wq + (f.x0 + 1));
+                // d sigma / d(ix, iy, iz) restricted to this lane's z-plane
+                const float gx_ = wz * (f.wy0 * (d4.y - d4.x) + f.wy1 * (d4.w - d4.z));
+                const float gy_ = wz * (f.wx0 * (d4.z - d4.x) + f.wx1 * (d4.w - d4.y));
+                const float pl = f.wx0 * f.wy0 * d4.x + f.wx1 * f.wy0 * d4.y + f.wx0 * f.wy1 * d4.z + f.wx1 * f.wy1 * d4.w;
+                const float gz_ = c ? pl : -pl;
+                const float px = dsig * gx_ * sx, py = dsig * gy_ * sy, pz = dsig * gz_ * sz;
+                go0 += px;
+                go1 += py;
+                go2 += pz;
+                gd0 = fmaf(z, px, gd0);
+                gd1 = fmaf(z, py, gd1);
+                gd2 = fmaf(z, pz, gd2);
+            }
         }
     }
     __syncwarp();
 
     // ---- camera gradient: 12 floats per view, reduced over the CTA ----
     if (need_cam) {
-        const float u = static_cast<float>(j) + 0.5f, v = static_cast<float>(i) + 0.5f;
-        float g12[12] = {go0, go1, go2, gd0 * u, gd0 * v, gd0, gd1 * u, gd1 * v, gd1, gd2 * u, gd2 * v, gd2};
-        const int lane = threadIdx.x & 31;
+        const float u = static_cast<float>(j) + 0.5f, vv = static_cast<float>(i) + 0.5f;
+        float g12[12] = {go0, go1, go2, gd0 * u, gd0 * vv, gd0, gd1 * u, gd1 * vv, gd1, gd2 * u, gd2 * vv, gd2};
 #pragma unroll
         for (int e = 0; e < 12; ++e) {
             float x = valid ? g12[e] : 0.f;
@@ -432,37 +441,50 @@ extern "C" int forge_raymarch_fwd(const float* feat_pad, const float* dens_quad,
         return fail(fn, "feat_pad must be 32-byte aligned, dens_quad / out_feat 16-byte aligned");
     const int tiles_x = (S_w + 15) / 16, tiles_y = (S_h + 7) / 8;
     dim3 grid(tiles_x * tiles_y, N);
-    raymarch_fwd_kernel<<<grid, kRmThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        feat_pad, reinterpret_cast<const float4*>(dens_quad), view2vol, cam12, zs, out_feat, out_sil, out_depth, D, H, W,
-        S_h, S_w, P, tiles_x);
+    static const int min_blocks = [] {          // tuning knob (development): resident CTAs per SM the kernel is built for
+        const char* e = getenv("FORGE_K1_MINBLOCKS");
+        return e ? atoi(e) : 3;         // measured on B200, cfg-2: 2 -> 0.411 ms, 3 -> 0.395 ms, 4 -> 0.394 ms
+    }();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float4* dq = reinterpret_cast<const float4*>(dens_quad);
+    if (min_blocks == 3)
+        raymarch_fwd_kernel<3><<<grid, kRmThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil,
+                                                            out_depth, D, H, W, S_h, S_w, P, tiles_x);
+    else if (min_blocks == 4)
+        raymarch_fwd_kernel<4><<<grid, kRmThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil,
+                                                            out_depth, D, H, W, S_h, S_w, P, tiles_x);
+    else
+        raymarch_fwd_kernel<2><<<grid, kRmThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil,
+                                                            out_depth, D, H, W, S_h, S_w, P, tiles_x);
     return check_launch(fn);
 }
 
-extern "C" int forge_raymarch_bwd(const float* feat_pad, const float* dens, const int* view2vol, const float* cam12,
-                                  const float* zs, const float* g_feat, const float* g_sil, const float* g_depth,
-                                  float* grad_feat_pad, float* grad_dens, float* grad_cam12, int N, int V, int D, int H,
-                                  int W, int S_h, int S_w, int P, void* stream) {
+extern "C" long long forge_raymarch_bwd_workspace(int N, int S_h, int S_w, int P) {
+    using namespace forge;
+    if (N <= 0 || S_h <= 0 || S_w <= 0 || P <= 0) return 0;
+    const long long tiles = static_cast<long long>((S_w + 15) / 16) * ((S_h + 7) / 8);
+    return tiles * N * P * 3 * kRaysPerCta * static_cast<long long>(sizeof(float));
+}
+
+extern "C" int forge_raymarch_bwd(const float* feat_pad, const float* dens_quad, const int* view2vol,
+                                  const float* cam12, const float* zs, const float* g_feat, const float* g_sil,
+                                  const float* g_depth, float* grad_feat_pad, float* grad_dens_pad, float* grad_cam12,
+                                  float* workspace, int N, int V, int D, int H, int W, int S_h, int S_w, int P,
+                                  void* stream) {
     using namespace forge;
     const char* fn = "forge_raymarch_bwd";
-    if (!feat_pad || !dens || !view2vol || !cam12 || !zs || !g_feat || !g_sil) return fail(fn, "null pointer");
-    if (!grad_feat_pad && !grad_dens && !grad_cam12) return 0;
+    if (!feat_pad || !dens_quad || !view2vol || !cam12 || !zs || !g_feat || !g_sil) return fail(fn, "null pointer");
+    if (!grad_feat_pad && !grad_dens_pad && !grad_cam12) return 0;
+    if (!workspace) return fail(fn, "null workspace (size it with forge_raymarch_bwd_workspace)");
     if (int e = raymarch_check(fn, N, V, D, H, W, S_h, S_w, P)) return e;
-    if (!aligned16(feat_pad) || !aligned16(g_feat) || (grad_feat_pad && !aligned16(grad_feat_pad)))
-        return fail(fn, "feat_pad / g_feat / grad_feat_pad must be 16-byte aligned");
-    const size_t smem = sizeof(float) * (static_cast<size_t>(P) + 12 + 12 * (kRmThreads / 32) +
-                                         3 * static_cast<size_t>(P) * kRaysPerCta);
-    if (smem > 227 * 1024) return fail(fn, "n_pts_per_ray too large for the backward pass (max 300)");
-    static thread_local size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(raymarch_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) return fail(fn, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-        smem_set = smem;
-    }
-    const int tiles_x = (S_w + 7) / 8, tiles_y = (S_h + 7) / 8;
+    if (P > kMaxP) return fail(fn, "n_pts_per_ray exceeds 512");
+    if ((reinterpret_cast<uintptr_t>(feat_pad) & 31u) || !aligned16(dens_quad) || !aligned16(g_feat) ||
+        (grad_feat_pad && !aligned16(grad_feat_pad)))
+        return fail(fn, "feat_pad must be 32-byte aligned, dens_quad / g_feat / grad_feat_pad 16-byte aligned");
+    const int tiles_x = (S_w + 15) / 16, tiles_y = (S_h + 7) / 8;
     dim3 grid(tiles_x * tiles_y, N);
-    raymarch_bwd_kernel<<<grid, kRmThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float4*>(feat_pad), dens, view2vol, cam12, zs, reinterpret_cast<const float4*>(g_feat),
-        g_sil, g_depth, grad_feat_pad, grad_dens, grad_cam12, D, H, W, S_h, S_w, P, tiles_x);
+    raymarch_bwd_kernel<<<grid, kRmThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        feat_pad, reinterpret_cast<const float4*>(dens_quad), view2vol, cam12, zs, g_feat, g_sil, g_depth, grad_feat_pad,
+        grad_dens_pad, grad_cam12, workspace, D, H, W, S_h, S_w, P, tiles_x);
     return check_launch(fn);
 }

@@ -125,7 +125,7 @@ class _Raymarch(torch.autograd.Function):
             _lib.call("forge_raymarch_fwd", _ptr(feat_pad), _ptr(dens_quad), _ptr(view2vol), _ptr(cam12), _ptr(zs),
                       _ptr(out), _ptr(sil), _ptr(depth), N, V, D, H, W, S_h, S_w, zs.numel(), _stream(feat))
         if any(ctx.needs_input_grad[:3]):
-            ctx.save_for_backward(feat_pad, _f32c(dens), cam12, view2vol, zs)
+            ctx.save_for_backward(feat_pad, dens_quad, cam12, view2vol, zs)
         ctx.dims = (N, V, D, H, W, S_h, S_w)
         ctx.render_depth = render_depth
         ctx.feat_cl = _feat_layout(feat)[1]
@@ -138,7 +138,7 @@ class _Raymarch(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, g_sil, g_depth):
-        feat_pad, dens, cam12, view2vol, zs = ctx.saved_tensors
+        feat_pad, dens_quad, cam12, view2vol, zs = ctx.saved_tensors
         N, V, D, H, W, S_h, S_w = ctx.dims
         dev = feat_pad.device
         need_f, need_d, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
@@ -146,22 +146,24 @@ class _Raymarch(torch.autograd.Function):
         g_sil = torch.zeros(N, S_h, S_w, device=dev) if g_sil is None else _f32c(g_sil)
         g_depth = _f32c(g_depth) if (ctx.render_depth and g_depth is not None) else None
         gfp = torch.zeros_like(feat_pad) if need_f else None
-        gd = torch.zeros(ctx.dens_shape, dtype=torch.float32, device=dev) if need_d else None
+        gdp = torch.zeros(V, D + 2, H + 2, W + 2, dtype=torch.float32, device=dev) if need_d else None
         gc = torch.zeros_like(cam12) if need_c else None
-        gf = None
+        gf = gd = None
         if need_f or need_d or need_c:
+            P = zs.numel()
+            ws = torch.empty(_lib.load().forge_raymarch_bwd_workspace(N, S_h, S_w, P) // 4, dtype=torch.float32, device=dev)
             with torch.cuda.device(dev):
-                _lib.call("forge_raymarch_bwd", _ptr(feat_pad), _ptr(dens), _ptr(view2vol), _ptr(cam12), _ptr(zs),
-                          _ptr(g_out), _ptr(g_sil), _ptr(g_depth), _ptr(gfp), _ptr(gd), _ptr(gc),
-                          N, V, D, H, W, S_h, S_w, zs.numel(), _stream(feat_pad))
+                _lib.call("forge_raymarch_bwd", _ptr(feat_pad), _ptr(dens_quad), _ptr(view2vol), _ptr(cam12), _ptr(zs),
+                          _ptr(g_out), _ptr(g_sil), _ptr(g_depth), _ptr(gfp), _ptr(gdp), _ptr(gc), _ptr(ws),
+                          N, V, D, H, W, S_h, S_w, P, _stream(feat_pad))
                 if need_f:
-                    if ctx.feat_cl:
-                        gf_cl = torch.empty(V, D, H, W, 16, dtype=torch.float32, device=dev)
-                        _lib.call("forge_unpack_volume_grad", _ptr(gfp), _ptr(gf_cl), 1, V, D, H, W, _stream(feat_pad))
-                        gf = gf_cl.permute(0, 4, 1, 2, 3)
+                    if ctx.feat_cl:     # interior of the padded gradient, viewed in the caller's layout (no copy)
+                        gf = gfp[:, 1:-1, 1:-1, 1:-1, :].permute(0, 4, 1, 2, 3)
                     else:
                         gf = torch.empty(ctx.feat_shape, dtype=torch.float32, device=dev)
                         _lib.call("forge_unpack_volume_grad", _ptr(gfp), _ptr(gf), 0, V, D, H, W, _stream(feat_pad))
+            if need_d:
+                gd = gdp[:, 1:-1, 1:-1, 1:-1].reshape(ctx.dens_shape)
         return gf, gd, gc, None, None, None, None, None
 
 

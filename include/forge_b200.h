@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 4
+#define FORGE_ABI_VERSION 6
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -66,16 +66,20 @@ int forge_raymarch_fwd(const float* feat_pad, const float* dens_quad, const int*
                        float* out_depth, int N, int V, int D, int H, int W, int S_h, int S_w, int P,
                        void* stream);
 
-/* Backward of forge_raymarch_fwd.  g_* are the upstream gradients (g_depth may be NULL).  Reads the
- * padded features and the PLAIN density volume dens [V][D][H][W].  grad_feat_pad (feat_pad layout)
- * and grad_dens [V][D][H][W] are ACCUMULATED into (caller zeroes them); either may be NULL to skip
- * that gradient (pose-only refinement, reference kubric_eval.py:450-504).  grad_cam12 [N][12] is
- * accumulated into (caller zeroes), may be NULL.  Replaces the autograd graph PyTorch builds
- * through the sequence named above. */
-int forge_raymarch_bwd(const float* feat_pad, const float* dens, const int* view2vol, const float* cam12,
-                       const float* zs, const float* g_feat, const float* g_sil, const float* g_depth,
-                       float* grad_feat_pad, float* grad_dens, float* grad_cam12,
-                       int N, int V, int D, int H, int W, int S_h, int S_w, int P, void* stream);
+/* Backward of forge_raymarch_fwd on the same packed inputs.  g_* are the upstream gradients
+ * (g_depth may be NULL).  grad_feat_pad (feat_pad layout) and grad_dens_pad [V][D+2][H+2][W+2]
+ * (zero-bordered, voxel (z,y,x) at (z+1,y+1,x+1)) are ACCUMULATED into (caller zeroes them);
+ * either may be NULL to skip that gradient (pose-only refinement, reference
+ * kubric_eval.py:450-504).  grad_cam12 [N][12] is accumulated into (caller zeroes), may be NULL.
+ * Replaces the autograd graph PyTorch builds through the sequence named above. */
+int forge_raymarch_bwd(const float* feat_pad, const float* dens_quad, const int* view2vol,
+                       const float* cam12, const float* zs, const float* g_feat, const float* g_sil,
+                       const float* g_depth, float* grad_feat_pad, float* grad_dens_pad, float* grad_cam12,
+                       float* workspace, int N, int V, int D, int H, int W, int S_h, int S_w, int P,
+                       void* stream);
+/* Bytes of caller-owned scratch forge_raymarch_bwd needs (per-ray sigma_k, a_k, T_k between its two
+ * passes; uninitialised is fine). */
+long long forge_raymarch_bwd_workspace(int N, int S_h, int S_w, int P);
 
 /* ---- K2: affine feature-volume resample ---------------------------------------------------
  * Replaces models/rotate.py:127-141: materialised homogeneous grid, matmul with T^T, divide by
