@@ -25,9 +25,11 @@ _SIGNATURES = {
     "forge_raymarch_bwd_workspace": (_c.c_longlong, [_I] * 4),
     "forge_rotate_fwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F] + [_I] * 5 + [_F]),
     "forge_rotate_bwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F, _F, _F] + [_I] * 5 + [_F]),
+    "forge_decoder_wpack_floats": (_c.c_int, []),
+    "forge_decoder_fwd": (_c.c_int, [_F, _F, _F, _I, _I, _I, _F]),
     "forge_sample_points": (_c.c_int, [_F, _I, _I, _I, _I, _I, _F, _F, _F]),
 }
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _lock = threading.Lock()
 _lib = None

@@ -68,6 +68,11 @@ class VolRender(nn.Module):
             nn.Conv2d(8, 3, kernel_size=self.k_size, stride=1, padding=self.pad_size),
         )
         self._zs = {}
+        # decoder arithmetic: None = fp32 like the reference; torch.bfloat16 runs conv_rgb under autocast on
+        # the tensor cores (BASELINE.json configs[2] "bf16 decoder"; RGB then deviates ~1e-2, not 1e-4)
+        self.decoder_dtype = None
+        self.fused_decoder = True
+        self._wpack = None
 
     # checkpoints written with older PyTorch3D carry the ray sampler's grid buffer; ignore it
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
@@ -125,8 +130,7 @@ class VolRender(nn.Module):
         density_3d: [B,1,D,H,W]
         '''
         feat, sil, depth, R, T, K = self.render_features(camera_params, feature_3d, density_3d, render_depth, view2vol)
-        rendered_imgs = feat.permute(0, 3, 1, 2)                      # NCHW view of the NHWC kernel output
-        rendered_imgs = F.relu(self.conv_rgb(rendered_imgs))
+        rendered_imgs = self.decode(feat)
         rendered_silhouettes = F.interpolate(sil.unsqueeze(1), size=[self.img_size] * 2, mode='bilinear')
         if render_depth:
             rendered_depth = F.interpolate(depth.unsqueeze(1), size=[self.img_size] * 2, mode='bilinear')
@@ -142,6 +146,27 @@ class VolRender(nn.Module):
                 return rendered_imgs, rendered_silhouettes, rendered_depth
             else:
                 return rendered_imgs, rendered_silhouettes
+
+    def _decoder_pack(self, device):
+        """BN-folded weight pack for the fused decoder, rebuilt only when a parameter / buffer changed."""
+        tensors = list(self.conv_rgb.parameters()) + list(self.conv_rgb.buffers())
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._wpack is None or self._wpack[0] != key:
+            self._wpack = (key, ops.pack_decoder_weights(self.conv_rgb))
+        return self._wpack[1]
+
+    def decode(self, feat_nhwc):
+        """[N,S,S,16] composited features -> relu(conv_rgb(.)) [N,3,2S,2S] (reference :73).
+        eval mode, fp32, k_size 5: one fused kernel; training mode (batch-statistics BN) or a
+        non-default decoder: the module's own cuDNN convs on the NHWC buffer."""
+        if (self.fused_decoder and not self.training and self.decoder_dtype is None and self.k_size == 5
+                and feat_nhwc.is_cuda):
+            return ops.decoder_fused(feat_nhwc, self._decoder_pack(feat_nhwc.device), self.conv_rgb)
+        x = feat_nhwc.permute(0, 3, 1, 2)                             # NCHW view of the NHWC kernel output
+        if self.decoder_dtype is None:
+            return F.relu(self.conv_rgb(x))
+        with torch.autocast('cuda', dtype=self.decoder_dtype):
+            return F.relu(self.conv_rgb(x)).float()
 
     def proj_origin(self, camera_params, device):
         K = self._halve_K(camera_params).to(device)

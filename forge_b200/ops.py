@@ -219,3 +219,59 @@ def rotate_resample(vox_cl, affine12, jobs, gx, gy, gz, gmax, n_dst):
     _require_cuda(vox_cl, affine12, jobs, gx, gy, gz)
     return _Rotate.apply(_f32c(vox_cl), _f32c(affine12), jobs.int().contiguous(), _f32c(gx), _f32c(gy), _f32c(gz),
                          float(gmax), int(n_dst))
+
+
+# ---- fused decoder -----------------------------------------------------------------------------
+def pack_decoder_weights(conv_rgb):
+    """BN-folded weight pack for forge_decoder_fwd from the reference-shaped ``conv_rgb`` Sequential
+    (ConvT2d, BN, LReLU, Conv2d, BN, LReLU, Conv2d) in eval mode; layout documented in forge_b200.h."""
+    ct, bn1, _, c2, bn2, _, c3 = conv_rgb
+    with torch.no_grad():
+        s1 = bn1.weight / torch.sqrt(bn1.running_var + bn1.eps)
+        s2 = bn2.weight / torch.sqrt(bn2.running_var + bn2.eps)
+        wt = ct.weight * s1.view(1, 16, 1, 1)                                   # [ci, co, 6, 6]
+        w1 = torch.stack([torch.stack([wt[:, :, py::2, px::2].permute(2, 3, 0, 1) for px in (0, 1)]) for py in (0, 1)])
+        w2 = (c2.weight * s2.view(8, 1, 1, 1)).permute(2, 3, 1, 0)               # [ky, kx, ci, co]
+        w3 = torch.zeros(5, 5, 8, 4, dtype=torch.float32, device=ct.weight.device)
+        w3[..., :3] = c3.weight.permute(2, 3, 1, 0)
+        b1 = (ct.bias - bn1.running_mean) * s1 + bn1.bias
+        b2 = (c2.bias - bn2.running_mean) * s2 + bn2.bias
+        b3 = torch.cat([c3.bias, c3.bias.new_zeros(1)])
+        pack = torch.cat([t.reshape(-1).float() for t in (w1, w2, w3, b1, b2, b3)]).contiguous()
+    assert pack.numel() == _lib.load().forge_decoder_wpack_floats()
+    return pack
+
+
+class _Decoder(torch.autograd.Function):
+    """Fused inference decoder; the backward pass re-runs the module's own convs under autograd (cuDNN)."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, wpack, conv_rgb):
+        N, Sh, Sw, _ = x_nhwc.shape
+        rgb = torch.empty(N, 3, 2 * Sh, 2 * Sw, dtype=torch.float32, device=x_nhwc.device)
+        with torch.cuda.device(x_nhwc.device):
+            _lib.call("forge_decoder_fwd", _ptr(x_nhwc), _ptr(wpack), _ptr(rgb), N, Sh, Sw, _stream(x_nhwc))
+        ctx.conv_rgb = conv_rgb
+        ctx.save_for_backward(x_nhwc)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g):
+        (x_nhwc,) = ctx.saved_tensors
+        with torch.enable_grad():
+            xi = x_nhwc.detach().requires_grad_(True)
+            y = torch.relu(ctx.conv_rgb(xi.permute(0, 3, 1, 2)))
+            params = [p for p in ctx.conv_rgb.parameters() if p.requires_grad]
+            grads = torch.autograd.grad(y, [xi] + params, g, allow_unused=True)
+        for p, gp in zip(params, grads[1:]):        # weights are not Function inputs: accumulate like autograd would
+            if gp is not None:
+                p.grad = gp if p.grad is None else p.grad + gp
+        return grads[0], None, None
+
+
+def decoder_fused(x_nhwc, wpack, conv_rgb):
+    """x [N,S,S,16] NHWC -> relu(conv_rgb(x)) [N,3,2S,2S] through the fused kernel (eval-mode BN)."""
+    _require_cuda(x_nhwc, wpack)
+    if x_nhwc.shape[-1] != 16:
+        raise ValueError("the decoder input must have 16 channels")
+    return _Decoder.apply(_f32c(x_nhwc), wpack, conv_rgb)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 6
+#define FORGE_ABI_VERSION 7
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -80,6 +80,20 @@ int forge_raymarch_bwd(const float* feat_pad, const float* dens_quad, const int*
 /* Bytes of caller-owned scratch forge_raymarch_bwd needs (per-ray sigma_k, a_k, T_k between its two
  * passes; uninitialised is fine). */
 long long forge_raymarch_bwd_workspace(int N, int S_h, int S_w, int P);
+
+/* ---- fused decoder ---------------------------------------------------------------------------
+ * relu(conv_rgb(x)) of models/volume_render.py:29-37,73 for inference (BatchNorm in eval mode):
+ * ConvTranspose2d(16,16,k6,s2,p2)+BN+LeakyReLU -> Conv2d(16,8,k5,p2)+BN+LeakyReLU -> Conv2d(8,3,k5,p2)
+ * -> ReLU in one kernel; the two intermediate images stay in shared memory.
+ *   x_nhwc [N][S_h][S_w][16] (the raymarcher's out_feat)  ->  rgb_nchw [N][3][2 S_h][2 S_w]
+ *   wpack: forge_decoder_wpack_floats() floats = BN-folded weights
+ *     W1[py][px][ty][tx][ci][co] = Wt[ci][co][py+2ty][px+2tx] * s1[co]      (4*9*16*16)
+ *     W2[ky][kx][ci][co]         = W2[co][ci][ky][kx] * s2[co]              (25*16*8)
+ *     W3[ky][kx][ci][4]          = W3[co][ci][ky][kx], co = 3 zero          (25*8*4)
+ *     b1[16] = (bt - mean1) s1 + beta1,  b2[8] likewise,  b3[4]             s = gamma / sqrt(var + eps) */
+int forge_decoder_wpack_floats(void);
+int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float* rgb_nchw, int N, int S_h, int S_w,
+                      void* stream);
 
 /* ---- K2: affine feature-volume resample ---------------------------------------------------
  * Replaces models/rotate.py:127-141: materialised homogeneous grid, matmul with T^T, divide by

@@ -257,3 +257,62 @@ def test_cpu_inputs_fail_loudly():
         m(dict(R=inp['R'], T=inp['T'], K=inp['K']), inp['feat'], inp['dens'])
     with pytest.raises(RuntimeError, match="CUDA"):
         Rotate_world(syn.make_config())(torch.zeros(1, 2, 4, 8, 8, 8), torch.eye(4).repeat(1, 2, 1, 1), grid_size=8)
+
+
+def test_streamed_renderer_matches_direct_call():
+    """Host-to-host pipeline (3 streams, batches in flight) returns exactly what the direct call returns."""
+    from forge_b200.pipeline import StreamedRenderer
+    cfg = syn.make_config(img_size=64, n_pts_per_ray=24)
+    m = VolRender(cfg).to(DEV).eval()
+    batches = [syn.render_inputs(2, 3, 64, 16, seed=s) for s in range(5)]
+    sr = StreamedRenderer(m, 2, 6, 16, depth=2)
+    outs = []
+    for b in batches:
+        pin = {k: v.pin_memory() for k, v in b.items()}
+        o = (torch.empty(6, 32, 32, 16).pin_memory(), torch.empty(6, 32, 32).pin_memory(), torch.empty(6, 32, 32).pin_memory())
+        sr.submit(pin['feat'], pin['dens'], pin['R'], pin['T'], pin['K'], pin['view2vol'], *o)
+        outs.append((pin, o))
+    sr.drain()
+    for b, (pin, o) in zip(batches, outs):
+        with torch.no_grad():
+            f, s, d, _, _, _ = m.render_features(dict(R=b['R'], T=b['T'], K=b['K'].clone()), b['feat'].to(DEV),
+                                                 b['dens'].to(DEV), True, view2vol=b['view2vol'])
+        assert torch.equal(o[0], f.cpu()) and torch.equal(o[1], s.cpu()) and torch.equal(o[2], d.cpu())
+
+
+@pytest.mark.parametrize("N,S", [(2, 16), (1, 21), (3, 64)])
+def test_fused_decoder_matches_module_convs(N, S):
+    """forge_decoder_fwd == relu(conv_rgb(x)) in eval mode (strict fp32 cuDNN), incl. ragged tiles."""
+    torch.manual_seed(N * 100 + S)
+    m = VolRender(syn.make_config(img_size=2 * S, n_pts_per_ray=8)).to(DEV)
+    for mod in m.conv_rgb:
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.3)
+            mod.running_var.uniform_(0.5, 2.0)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.2)
+    m.eval()
+    x = torch.randn(N, S, S, 16, device=DEV)
+    with torch.no_grad():
+        fused = m.decode(x)
+        m.fused_decoder = False
+        ref = m.decode(x)
+    assert fused.shape == ref.shape == (N, 3, 2 * S, 2 * S)
+    assert (fused - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    # weight-pack cache follows in-place parameter updates
+    m.fused_decoder = True
+    with torch.no_grad():
+        m.conv_rgb[6].bias.add_(0.5)
+        fused2 = m.decode(x)
+        m.fused_decoder = False
+        ref2 = m.decode(x)
+    assert (fused2 - ref2).abs().max().item() <= 2e-5 * max(1.0, ref2.abs().max().item())
+    # gradients flow through the fused forward (backward re-runs the module convs)
+    m.fused_decoder = True
+    xg = x.clone().requires_grad_(True)
+    m.decode(xg).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    m.fused_decoder = False
+    m.zero_grad()
+    m.decode(xr).sum().backward()
+    assert torch.allclose(xg.grad, xr.grad, atol=1e-4, rtol=1e-4)

@@ -109,7 +109,27 @@ def main():
                 cam = dict(R=inp['R'], T=inp['T'], K=inp['K'].clone())
                 return m(cam, inp['feat'], inp['dens'], render_depth=True, return_origin_proj=True, view2vol=inp['view2vol'])
             ms, best = timeit(full, args.reps, flush)
-            report("VolRender.forward (relayout+K1+conv_rgb cuDNN+upsample)", ms, best, None, Mrays_per_s=round(rays / ms / 1e3, 1))
+            report("VolRender.forward (pack+K1+conv_rgb cuDNN+upsample)", ms, best, None, Mrays_per_s=round(rays / ms / 1e3, 1))
+            x = torch.randn(N, S, S, 16, device=DEV)
+            ms, best = timeit(lambda: m.decode(x), args.reps, flush)
+            report("decoder FUSED fp32 kernel (forge_decoder_fwd)", ms, best, None,
+                   fp32_TFLOPs=round(N * (2 * S) ** 2 * 6104 * 2 / ms / 1e9, 2))
+            m.fused_decoder = False
+            for name, setup in (("fp32 (TF32 allowed, torch default)", lambda: None),
+                                ("fp32 strict (allow_tf32=False)", lambda: setattr(torch.backends.cudnn, 'allow_tf32', False)),
+                                ("bf16 autocast", lambda: setattr(m, 'decoder_dtype', torch.bfloat16))):
+                setup()
+                ms, best = timeit(lambda: m.decode(x), args.reps, flush)
+                report("decoder conv_rgb cuDNN, " + name, ms, best, None)
+            m.decoder_dtype = None
+            m.fused_decoder = True
+            torch.backends.cudnn.allow_tf32 = True
+            xc = x.permute(0, 3, 1, 2).contiguous()
+            ms, best = timeit(lambda: torch.relu(m.conv_rgb(xc)), args.reps, flush)
+            report("decoder conv_rgb cuDNN, NCHW-contiguous input", ms, best, None)
+            sil = torch.randn(N, S, S, device=DEV)
+            ms, best = timeit(lambda: torch.nn.functional.interpolate(sil.unsqueeze(1), size=[img, img], mode='bilinear'), args.reps, flush)
+            report("bilinear x2 upsample of one [N,1,S,S] map (torch)", ms, best, None)
         if want("k2"):
             C, n = 128, D // 2
             vox, poses = syn.rotate_inputs(b, t, C, n, seed=1, device=DEV)
