@@ -265,6 +265,7 @@ class _Decoder(torch.autograd.Function):
             grads = torch.autograd.grad(y, [xi] + params, g, allow_unused=True)
         for p, gp in zip(params, grads[1:]):        # weights are not Function inputs: accumulate like autograd would
             if gp is not None:
+                gp = gp.contiguous()
                 p.grad = gp if p.grad is None else p.grad + gp
         return grads[0], None, None
 
