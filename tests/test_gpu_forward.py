@@ -320,16 +320,16 @@ def test_fused_decoder_matches_module_convs(N, S):
 
 def test_raymarch_cfg4_stress_vs_oracle():
     """BASELINE.json configs[3] geometry: 256x256 rays per view (img 512), 128^3 voxels, 128 samples;
-    one object, 5 views, oracle evaluated view by view on the GPU (same ATen ops as the reference)."""
+    one object, 2 views, oracle evaluated view by view on the GPU (same ATen ops as the reference)."""
     img, vol, P = 512, 128, 128
-    inp = syn.render_inputs(1, 5, img, vol, seed=11)
+    inp = syn.render_inputs(1, 2, img, vol, seed=11)
     m = VolRender(syn.make_config(img_size=img, n_pts_per_ray=P)).to(DEV).eval()
     feat_d, dens_d = inp['feat'].to(DEV), inp['dens'].to(DEV)
     with torch.no_grad():
         feat, sil, depth, _, _, Kh = m.render_features(dict(R=inp['R'].clone(), T=inp['T'].clone(), K=inp['K'].clone()),
                                                        feat_d, dens_d, True, view2vol=inp['view2vol'])
         worst = 0.0
-        for v in range(5):
+        for v in range(2):
             f, o, d = cf.raymarch(inp['R'][v:v + 1].to(DEV), inp['T'][v:v + 1].to(DEV), Kh[v:v + 1], feat_d, dens_d,
                                   img // 2, P, 0.5, 2.0, 1.0)
             worst = max(worst, (feat[v:v + 1] - f).abs().max().item(), (sil[v:v + 1] - o).abs().max().item(),
@@ -342,21 +342,27 @@ def test_raymarch_cfg4_stress_vs_oracle():
         cam = lambda: dict(R=inp['R'].clone(), T=inp['T'].clone(), K=inp['K'].clone())   # noqa: E731
         r2, s2, _, _, _, _ = m.render_features(cam(), f2, dens_d, True, view2vol=inp['view2vol'])
         r12, s12, _, _, _, _ = m.render_features(cam(), 0.5 * feat_d - 2.0 * f2, dens_d, True, view2vol=inp['view2vol'])
-    assert torch.equal(s2, sil) and torch.equal(s12, sil)                 # silhouette/depth ignore the features
-    assert (r12 - (0.5 * feat - 2.0 * r2)).abs().max().item() <= 1e-4
+    same_sil = bool(torch.equal(s2, sil)) and bool(torch.equal(s12, sil))   # silhouette ignores the features
+    lin_err = (r12 - (0.5 * feat - 2.0 * r2)).abs().max().item()
+    assert same_sil
+    assert lin_err <= 1e-4
 
 
 def test_rotate_cfg4_stress_vs_oracle():
     """64^3 x 128-channel volumes (the fusion grid of configs[3])."""
-    vox, poses = syn.rotate_inputs(1, 3, 128, 64, seed=12)
+    vox, poses = syn.rotate_inputs(1, 2, 128, 64, seed=12)
     m = Rotate_world(syn.make_config()).to(DEV)
     with torch.no_grad():
         out = m(vox.to(DEV), poses.to(DEV), grid_size=64)
         ref = rp.rotate_world_forward(vox.to(DEV), poses.to(DEV), 64, 1.0)
-    assert (out - ref).abs().max().item() <= TOL
+    err = (out - ref).abs().max().item()
+    assert err <= TOL
     # idempotence of the passthrough + exact zero outside: a pure translation by more than the volume size empties it
     far = poses.clone()
     far[:, 1:, :3, 3] += 10.0
     with torch.no_grad():
         out2 = m(vox.to(DEV), far.to(DEV), grid_size=64)
-    assert torch.equal(out2[:, 0].cpu(), vox[:, 0]) and out2[:, 1:].abs().max().item() == 0.0
+    passthrough = bool(torch.equal(out2[:, 0], vox[:, 0].to(DEV)))
+    outside = out2[:, 1:].abs().max().item()
+    assert passthrough
+    assert outside == 0.0
