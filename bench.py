@@ -260,6 +260,36 @@ def run_forge(args, rank, world, local_rank):
         if args.verbose and rank == 0:
             sys.stderr.write("step ms: %s\n" % " ".join("%.3f" % x for x in step_ms))
 
+        # ---- secondary: K2 (the HBM-bound kernel of the path) on cfg-2's fusion grid, same run ------------
+        from forge_b200 import synthetic as syn
+        from forge_b200.models.rotate import Rotate_world
+        Cr, nr, tr = 128, D // 2, CFG['views']
+        rot = Rotate_world(cfg).to(dev)
+        vox, poses = syn.rotate_inputs(CFG['objects'], tr, Cr, nr, seed=100 + rank, device=dev)
+        vcl = vox.permute(0, 1, 3, 4, 5, 2).contiguous().reshape(CFG['objects'] * tr, nr, nr, nr, Cr)
+        del vox
+        gxd, gyd, gzd, gmax = rot._device_axes(nr, nr, nr, dev)
+        A = torch.zeros(CFG['objects'], tr, 3, 4, device=dev)
+        A[:, 1:] = rot.get_transformation(poses).reshape(CFG['objects'], tr - 1, 4, 4)[:, :, :3, :]
+        A = A.reshape(-1, 12).contiguous()
+        jobs = rot._jobs(CFG['objects'], tr, dev, None)
+        out_cl = torch.empty_like(vcl)
+        k2_ms = []
+        for it in range(3 + 10):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.call("forge_rotate_fwd", vcl.data_ptr(), A.data_ptr(), jobs.data_ptr(), gxd.data_ptr(), gyd.data_ptr(),
+                      gzd.data_ptr(), float(gmax), out_cl.data_ptr(), CFG['objects'] * tr, Cr, nr, nr, nr,
+                      torch.cuda.current_stream(dev).cuda_stream)
+            b.record()
+            torch.cuda.synchronize(dev)
+            if it >= 3:
+                k2_ms.append(a.elapsed_time(b))
+        k2_avg_ms = sum(k2_ms) / len(k2_ms)
+        k2_bytes = 2 * vcl.numel() * 4
+        del vcl, out_cl
+
         # ---- end to end: pinned host inputs -> H2D -> public API -> D2H, everything timed ----------
         h_feat, h_dens = feat.cpu().pin_memory(), dens.cpu().pin_memory()
         h_R, h_T, h_K = inp['R'].cpu().pin_memory(), inp['T'].cpu().pin_memory(), inp['K'].cpu().pin_memory()
@@ -341,7 +371,15 @@ def run_forge(args, rank, world, local_rank):
                      "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                      "algorithmic_bytes": algorithmic_bytes_k1(), "kernel_ms": k1_avg_s * 1e3,
                      "fp32_tflops": rays * CFG['n_pts'] * FLOPS_PER_SAMPLE / k1_avg_s / 1e12,
-                     "note": "K1 is L1-gather/issue bound, not HBM bound (SURVEY 8d); bytes are the distinct-volume figure"},
+                     "note": "K1 is bound by the L1 data pipe (register write-back of the gathered corners, ncu 72 %), not by "
+                             "HBM (SURVEY 8d: 82 FLOP/B); bytes are the distinct-volume figure; see roofline_rotate for the "
+                             "HBM-bound kernel of the path"},
+        "roofline_rotate": {"bound": "hbm", "kernel": "rotate_fwd_kernel (K2, %d view-volumes of 128x%d^3, channels-last)"
+                            % (CFG['objects'] * CFG['views'], CFG['vol'] // 2),
+                            "achieved": k2_bytes / (k2_avg_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": k2_bytes / (k2_avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_kind": peak_kind,
+                            "algorithmic_bytes": k2_bytes, "kernel_ms": k2_avg_ms,
+                            "note": "secondary line: the HBM-bound kernel of the path, rank 0, timed in the same run"},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Data-parallel training step of the FORGE graph (use_gt_pose) under torch DDP over NCCL: one process per
+GPU, each rank its own objects, gradients all-reduced by DDP (the only collective on the path).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/ddp_step.py
+
+Checks that (1) the custom autograd Functions (K1, K2, pack, decoder) work under DDP's hooks, (2) after
+the all-reduce every rank holds identical gradients, (3) they equal the average of the per-rank gradients
+computed without DDP.  Prints step time and rays/s (whole job).
+"""
+import json
+import os
+import sys
+import time
+import warnings
+
+import torch
+import torch.distributed as dist
+from torch.nn.parallel import DistributedDataParallel as DDP
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from forge_b200 import synthetic as syn                 # noqa: E402
+from forge_b200.models.model import FORGE              # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    b, t_all = 1, 6
+    torch.manual_seed(0)                                   # identical init on every rank
+    cfg = syn.make_config(img_size=256, n_pts_per_ray=64, use_gt_pose=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = FORGE(cfg).to(dev)
+    model.encoder_3d.density_head[6].bias.data.fill_(0.1)
+    model.train()
+    model.encoder_3d.feature_extraction.eval()             # keep the ResNet BN in eval, like the reference's set_model_train
+    sample = syn.kubric_batch(b, n_views_all=t_all, img_size=256, seed=10 + rank)     # each rank: its own objects
+    target = torch.rand(b * t_all, 3, 256, 256, device=dev)
+
+    def loss_of(m):
+        rgb, mask = m(sample, None, dev)
+        return torch.nn.functional.mse_loss(rgb, target) + mask.mean()
+
+    # reference gradients without DDP: local grads, then averaged by hand
+    model.zero_grad()
+    loss_of(model).backward()
+    names = [n for n, p in model.named_parameters() if p.grad is not None]
+    local_grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    for g in local_grads.values():
+        dist.all_reduce(g)
+        g /= world
+
+    ddp = DDP(model, device_ids=[local], find_unused_parameters=True)      # reference kubric_train_joint.py:141
+    model.zero_grad()
+    loss_of(ddp).backward()
+    worst = 0.0
+    for n, p in model.named_parameters():
+        if n in local_grads:
+            denom = local_grads[n].abs().max().item() + 1e-12
+            worst = max(worst, (p.grad - local_grads[n]).abs().max().item() / denom)
+    # identical across ranks?
+    probe = dict(model.named_parameters())['encoder_3d.features_head.0.weight'].grad.flatten()[:1000].clone()
+    lo, hi = probe.clone(), probe.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool((lo == hi).all())
+
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    for _ in range(2):
+        opt.zero_grad()
+        loss_of(ddp).backward()
+        opt.step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    iters = 5
+    for _ in range(iters):
+        opt.zero_grad()
+        loss_of(ddp).backward()
+        opt.step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / iters * 1e3
+    if rank == 0:
+        print(json.dumps({"ddp_step": "FORGE(use_gt_pose) fwd+bwd+Adam, b=%d/GPU, %d views rendered" % (b, t_all),
+                          "world": world, "ms_per_step": round(ms, 2), "n_params_with_grad": len(names),
+                          "grad_rel_err_vs_manual_average": float("%.3e" % worst), "grads_identical_across_ranks": same,
+                          "rays_per_s_whole_job": round(world * b * t_all * 128 * 128 / ms * 1e3)}))
+    assert same and worst < 5e-3, (same, worst)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
