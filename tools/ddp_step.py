@@ -57,11 +57,10 @@ def main():
     ddp = DDP(model, device_ids=[local], find_unused_parameters=True)      # reference kubric_train_joint.py:141
     model.zero_grad()
     loss_of(ddp).backward()
-    worst = 0.0
-    for n, p in model.named_parameters():
-        if n in local_grads:
-            denom = local_grads[n].abs().max().item() + 1e-12
-            worst = max(worst, (p.grad - local_grads[n]).abs().max().item() / denom)
+    # conv biases in front of a train-mode BN have analytically zero gradients (pure rounding noise), so the
+    # error is measured against the largest gradient entry of the whole model
+    gmax = max(g.abs().max().item() for g in local_grads.values())
+    worst = max((p.grad - local_grads[n]).abs().max().item() for n, p in model.named_parameters() if n in local_grads) / gmax
     # identical across ranks?
     probe = dict(model.named_parameters())['encoder_3d.features_head.0.weight'].grad.flatten()[:1000].clone()
     lo, hi = probe.clone(), probe.clone()
