@@ -78,3 +78,24 @@ def test_state_dict_keys_match_reference_layout():
     g = load_golden("volrender_small")
     VolRender(make_config(img_size=32, n_pts_per_ray=24)).load_state_dict(
         {k[3:]: v for k, v in g.items() if k.startswith('sd.')}, strict=True)
+
+
+def test_model_state_dict_matches_reference_tables():
+    """Every encoder_3d / render / rotate key (and shape) of the reference FORGE and FORGE_poseEstimator3D exists
+    here and vice versa; the remaining reference keys belong to the out-of-scope pose modules only."""
+    import json
+    import warnings
+    from forge_b200.synthetic import make_config
+    from forge_b200.models.model import FORGE
+    from forge_b200.models.model_single_pose_estimator import FORGE_poseEstimator3D
+    with open(os.path.join(ROOT, "tests", "golden", "reference_state_dict_shapes.json")) as fh:
+        ref = json.load(fh)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mine = {"FORGE": FORGE(make_config()).state_dict(), "FORGE_poseEstimator3D": FORGE_poseEstimator3D(make_config()).state_dict()}
+    for name, table in ref.items():
+        in_scope = {k: v for k, v in table.items() if k.split('.')[0] in ('encoder_3d', 'render', 'rotate')}
+        others = {k.split('.')[0] for k in table} - {'encoder_3d', 'render', 'rotate'}
+        assert others <= {'encoder_traj', 'encoder_traj_2d', 'pose_head'}
+        got = {k: list(v.shape) for k, v in mine[name].items()}
+        assert got == in_scope, (sorted(set(got) ^ set(in_scope))[:10])
