@@ -29,6 +29,28 @@ constexpr int WPACK_N = W1_N + W2_N + W3_N + 16 + 8 + 4;                        
 constexpr int SM_IN = IN_H * IN_RS, SM_L1 = L1_H * L1_RS, SM_L2 = L2_H * L2_RS;
 constexpr int kDecSmemFloats = SM_IN + SM_L1 + SM_L2 + WPACK_N;
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// one bulk async copy (TMA engine, SASS UBLKCP) global -> shared, completion on an mbarrier
+__device__ __forceinline__ void bulk_load_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spins = 0; !done; ++spins) {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (spins > (1 << 24)) __trap();     // a lost copy must fail loudly, not hang the GPU
+    }
+}
+
 __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : 0.01f * v; }
 
@@ -52,9 +74,15 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
     const int OH = 2 * Sh, OW = 2 * Sw;
     const int tid = threadIdx.x;
 
-    // ---- phase 0: weights + input tile (zeros outside the image) ----
-    for (int e = tid; e < WPACK_N / 4; e += kDecThreads)
-        reinterpret_cast<float4*>(sW1)[e] = __ldg(reinterpret_cast<const float4*>(wpack) + e);
+    // ---- phase 0: weights by one bulk async copy (53 KB, no register staging) overlapped with the
+    //      threads' own load of the input tile (zeros outside the image) ----
+    __shared__ __align__(8) unsigned long long wbar;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) bulk_load_g2s(sW1, wpack, WPACK_N * sizeof(float), &wbar);
     {
         const int iy0 = Y0 / 2 - 3, ix0 = X0 / 2 - 3;
         const float4* xin = reinterpret_cast<const float4*>(x) + static_cast<long long>(n) * Sh * Sw * 4;
@@ -67,6 +95,7 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
             *reinterpret_cast<float4*>(sIn + r * IN_RS + c * IN_PS + q4 * 4) = v;
         }
     }
+    mbar_wait(&wbar, 0);
     __syncthreads();
 
     // ---- phase 1: transposed conv 16 -> 16 over the 40x24 layer-1 tile; task = (parity class, co half,

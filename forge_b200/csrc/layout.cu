@@ -85,65 +85,92 @@ __global__ void sample_points_kernel(const float* __restrict__ pts, int M, int D
 }
 
 // ---- render-volume packing -------------------------------------------------------------------------
-// One CTA per padded (z, y) row of one volume: builds the zero-bordered channels-last feature row
-// [W+2][16] (from NCDHW through a shared-memory transpose, or from channels-last directly) and the
-// density-quad row [W+1][4].  HBM-bound: reads V*17*D*H*W*4 bytes, writes ~1.1x + 4x the density.
+// One CTA per group of kPackRows consecutive padded y-rows of one (volume, z): for every channel those input
+// rows are one contiguous run (kPackRows * W floats), read with 128-bit loads, transposed through shared
+// memory ([row][x][channel], x-stride 17 / row-stride = 2 mod 32 banks) and written as zero-bordered
+// channels-last rows [W+2][16] plus the density-quad rows [W+1][4].  HBM-bound: reads V*17*D*H*W*4 bytes,
+// writes ~1.1x that + 4x the density.
 constexpr int kPackThreads = 256;
+constexpr int kPackRows = 8;
 
 __global__ void __launch_bounds__(kPackThreads)
 pack_volume_kernel(const float* __restrict__ feat, int feat_cl, const float* __restrict__ dens,
-                   float* __restrict__ feat_pad, float4* __restrict__ dens_quad, int D, int H, int W) {
-    extern __shared__ float sm[];
+                   float* __restrict__ feat_pad, float4* __restrict__ dens_quad, int D, int H, int W, int ygroups) {
+    extern __shared__ __align__(16) float sm[];
     const int Wp = W + 2, Hp = H + 2, Wq = W + 1, Hq = H + 1;
-    float* tile = sm;                        // [16][W + 1]
-    float* d0 = sm + 16 * (W + 1);           // [W + 2]  density row (z, y-1... see below), x = -1 .. W
-    float* d1 = d0 + Wp;                     // [W + 2]
+    const int TS = W * 17 + 2;                          // floats per transposed row
+    float* tile = sm;                                   // [kPackRows][W][17]
+    float* drow = sm + kPackRows * TS;                  // [kPackRows + 1][W + 2] density rows y0-1 .. y0+kPackRows-1
     const int v = blockIdx.y;
-    const int zp = blockIdx.x / Hp, yp = blockIdx.x - zp * Hp;
-    const int z = zp - 1, y = yp - 1;
+    const int zp = blockIdx.x / ygroups, yp0 = (blockIdx.x - zp * ygroups) * kPackRows;
+    const int z = zp - 1;
     const long long S = static_cast<long long>(D) * H * W;
     const bool zin = (z >= 0 && z < D);
-    const bool interior = zin && (y >= 0 && y < H);
+    // interior rows of this group: padded rows yp0 + ry with y = yp0 + ry - 1 in [0, H)
+    const int ry_lo = max(0, 1 - yp0), ry_hi = min(kPackRows, H + 1 - yp0);       // [ry_lo, ry_hi)
 
-    if (interior && !feat_cl) {
-        const float* src = feat + static_cast<long long>(v) * 16 * S + (static_cast<long long>(z) * H + y) * W;
-        for (int e = threadIdx.x; e < 16 * W; e += kPackThreads) {
-            const int ch = e / W, x = e - ch * W;
-            tile[ch * (W + 1) + x] = src[static_cast<long long>(ch) * S + x];
+    if (zin && !feat_cl && ry_hi > ry_lo) {
+        const int rows = ry_hi - ry_lo;
+        const float* base = feat + static_cast<long long>(v) * 16 * S + (static_cast<long long>(z) * H + (yp0 + ry_lo - 1)) * W;
+        if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15u) == 0) {
+            const int wq = W >> 2, per_ch = rows * wq;
+            for (int u = threadIdx.x; u < 16 * per_ch; u += kPackThreads) {
+                const int ch = u / per_ch, rem = u - ch * per_ch;
+                const int ry = rem / wq, xq = rem - ry * wq;
+                const float4 val = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(ch) * S + ry * W) + xq);
+                float* t = tile + (ry_lo + ry) * TS + (4 * xq) * 17 + ch;
+                t[0] = val.x;
+                t[17] = val.y;
+                t[34] = val.z;
+                t[51] = val.w;
+            }
+        } else {
+            const int per_ch = rows * W;
+            for (int u = threadIdx.x; u < 16 * per_ch; u += kPackThreads) {
+                const int ch = u / per_ch, rem = u - ch * per_ch;
+                const int ry = rem / W, x = rem - ry * W;
+                tile[(ry_lo + ry) * TS + x * 17 + ch] = __ldg(base + static_cast<long long>(ch) * S + ry * W + x);
+            }
         }
     }
-    // density rows y (d0) and y + 1 (d1) of plane z, zero outside the volume
-    for (int e = threadIdx.x; e < 2 * Wp; e += kPackThreads) {
-        const int which = e / Wp, xs = e - which * Wp;     // xs = x + 1
-        const int yy = y + which, x = xs - 1;
+    for (int e = threadIdx.x; e < (kPackRows + 1) * Wp; e += kPackThreads) {
+        const int ry = e / Wp, xs = e - ry * Wp;        // xs = x + 1
+        const int y = yp0 + ry - 1, x = xs - 1;
         float val = 0.f;
-        if (zin && yy >= 0 && yy < H && x >= 0 && x < W)
-            val = dens[static_cast<long long>(v) * S + (static_cast<long long>(z) * H + yy) * W + x];
-        (which ? d1 : d0)[xs] = val;
+        if (zin && y >= 0 && y < H && x >= 0 && x < W)
+            val = __ldg(dens + static_cast<long long>(v) * S + (static_cast<long long>(z) * H + y) * W + x);
+        drow[ry * Wp + xs] = val;
     }
     __syncthreads();
 
-    float* out = feat_pad + ((static_cast<long long>(v) * (D + 2) + zp) * Hp + yp) * Wp * 16;
-    if (interior) {
-        if (feat_cl) {
-            const float* src = feat + (static_cast<long long>(v) * S + (static_cast<long long>(z) * H + y) * W) * 16;
-            for (int e = threadIdx.x; e < Wp * 16; e += kPackThreads) {
-                const int xp = e >> 4;
-                out[e] = (xp >= 1 && xp <= W) ? src[e - 16] : 0.f;
-            }
-        } else {
-            for (int e = threadIdx.x; e < Wp * 16; e += kPackThreads) {
-                const int xp = e >> 4, ch = e & 15;
-                out[e] = (xp >= 1 && xp <= W) ? tile[ch * (W + 1) + xp - 1] : 0.f;
+    const int nrows = min(kPackRows, Hp - yp0);
+    // feature rows: nrows x (Wp * 4) float4, contiguous in feat_pad (consecutive padded rows follow each other)
+    float4* out = reinterpret_cast<float4*>(feat_pad + ((static_cast<long long>(v) * (D + 2) + zp) * Hp + yp0) * Wp * 16);
+    const int row4 = Wp * 4;
+    for (int u = threadIdx.x; u < nrows * row4; u += kPackThreads) {
+        const int ry = u / row4, e = u - ry * row4;
+        const int xp = e >> 2, c4 = (e & 3) * 4;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (zin && ry >= ry_lo && ry < ry_hi && xp >= 1 && xp <= W) {
+            if (feat_cl) {
+                const int y = yp0 + ry - 1;
+                o = __ldg(reinterpret_cast<const float4*>(feat + (static_cast<long long>(v) * S + (static_cast<long long>(z) * H + y) * W + xp - 1) * 16 + c4));
+            } else {
+                const float* t = tile + ry * TS + (xp - 1) * 17 + c4;
+                o = make_float4(t[0], t[1], t[2], t[3]);
             }
         }
-    } else {
-        for (int e = threadIdx.x; e < Wp * 16; e += kPackThreads) out[e] = 0.f;
+        out[u] = o;
     }
-    if (yp <= H) {   // quad row yq = yp covers y = yp - 1 and y + 1 = yp
-        float4* q = dens_quad + ((static_cast<long long>(v) * (D + 2) + zp) * Hq + yp) * Wq;
-        for (int xq = threadIdx.x; xq < Wq; xq += kPackThreads)
-            q[xq] = make_float4(d0[xq], d0[xq + 1], d1[xq], d1[xq + 1]);
+    // density quads: row yq = yp covers y = yp - 1 (drow[ry]) and y + 1 = yp (drow[ry + 1]); rows yq <= H
+    const int qrows = min(kPackRows, Hq - yp0);
+    if (qrows > 0) {
+        float4* q = dens_quad + ((static_cast<long long>(v) * (D + 2) + zp) * Hq + yp0) * Wq;
+        for (int u = threadIdx.x; u < qrows * Wq; u += kPackThreads) {
+            const int ry = u / Wq, xq = u - ry * Wq;
+            const float* d0 = drow + ry * Wp, * d1 = d0 + Wp;
+            q[u] = make_float4(d0[xq], d0[xq + 1], d1[xq], d1[xq + 1]);
+        }
     }
 }
 
@@ -224,11 +251,19 @@ extern "C" int forge_pack_volume(const float* feat, int feat_channels_last, cons
     if (V <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(fn, "non-positive size");
     if (V > 65535) return fail(fn, "more than 65535 volumes in one launch");
     if (!aligned16(dens_quad)) return fail(fn, "dens_quad must be 16-byte aligned");
-    const size_t smem = sizeof(float) * (16 * (W + 1) + 2 * (W + 2));
-    if (smem > 48 * 1024) return fail(fn, "volume rows longer than 700 voxels are not supported");
-    dim3 grid((D + 2) * (H + 2), V);
+    if (!aligned16(feat_pad) || (feat_channels_last && !aligned16(feat))) return fail(fn, "feat_pad / feat must be 16-byte aligned");
+    const size_t smem = sizeof(float) * (kPackRows * (W * 17 + 2) + (kPackRows + 1) * (W + 2));
+    if (smem > 200 * 1024) return fail(fn, "volume rows longer than 360 voxels are not supported");
+    static thread_local size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(pack_volume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return fail(fn, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+        smem_set = smem;
+    }
+    const int ygroups = (H + 2 + kPackRows - 1) / kPackRows;
+    dim3 grid((D + 2) * ygroups, V);
     pack_volume_kernel<<<grid, kPackThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        feat, feat_channels_last, dens, feat_pad, reinterpret_cast<float4*>(dens_quad), D, H, W);
+        feat, feat_channels_last, dens, feat_pad, reinterpret_cast<float4*>(dens_quad), D, H, W, ygroups);
     return check_launch(fn);
 }
 

@@ -11,13 +11,21 @@
 // Phase 2: one thread per (voxel, channel vector): 4 broadcast LDS.128, 8 coalesced LDG.128,
 // 32 FFMA, 1 coalesced STG.128 -- the per-voxel scalar work is not replicated across the 32 channel
 // lanes, which is what kept v1 issue-bound at 36 % of HBM peak.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace forge {
 
 constexpr int kRotThreads = 256;
-constexpr int kTx = 8, kTy = 8, kTz = 4;            // output-voxel block per CTA
-constexpr int kTileVox = kTx * kTy * kTz;           // 256 = one voxel per thread in phase 1
+constexpr int kTileVox = 256;                       // output voxels per CTA = one voxel per thread in phase 1
+// output-voxel block per CTA, kTx * kTy * kTz == kTileVox (shape 0 = 8x8x4 is the default)
+struct TileShape {
+    int tx, ty, tz;
+};
+__host__ __device__ constexpr TileShape tile_shape(int id) {
+    return id == 1 ? TileShape{16, 4, 4} : id == 2 ? TileShape{4, 8, 8} : id == 3 ? TileShape{16, 16, 1} : id == 4 ? TileShape{32, 8, 1} : TileShape{8, 8, 4};
+}
 static_assert(kTileVox == kRotThreads, "phase 1 maps one thread to one voxel");
 
 struct RotJob {
@@ -67,7 +75,8 @@ struct RotTile {
 __device__ __forceinline__ void rotate_phase1(RotTile& s, float (*frac)[6], const float* __restrict__ affine, int m,
                                               const float* __restrict__ gx, const float* __restrict__ gy,
                                               const float* __restrict__ gz, float inv_max, int D, int H, int W,
-                                              int tx, int ty, int tz) {
+                                              int tx, int ty, int tz, const TileShape sh) {
+    const int kTx = sh.tx, kTy = sh.ty, kTz = sh.tz;
     if (threadIdx.x < 12) s.A[threadIdx.x] = affine[12 * m + threadIdx.x];
     __syncthreads();
     const int v = threadIdx.x;
@@ -99,12 +108,14 @@ __device__ __forceinline__ void rotate_phase1(RotTile& s, float (*frac)[6], cons
 }
 
 // CU = channel vectors per voxel (C/4 for float4, C for float)
-template <typename VecT>
+template <typename VecT, int kShape, bool kStream>
 __global__ void __launch_bounds__(kRotThreads, 4)
 rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine, const int* __restrict__ jobs,
                   const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ gz,
                   float inv_max, VecT* __restrict__ out, int CU, int D, int H, int W, int tiles_x, int tiles_y) {
     __shared__ __align__(16) RotTile s;
+    constexpr TileShape sh = tile_shape(kShape);
+    constexpr int kTx = sh.tx, kTy = sh.ty, kTz = sh.tz;
     const int m = blockIdx.y;
     const RotJob job = {jobs[3 * m], jobs[3 * m + 1], jobs[3 * m + 2]};
     const int tz = blockIdx.x / (tiles_x * tiles_y);
@@ -124,7 +135,7 @@ rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
         }
         return;
     }
-    rotate_phase1(s, nullptr, affine, m, gx, gy, gz, inv_max, D, H, W, tx, ty, tz);
+    rotate_phase1(s, nullptr, affine, m, gx, gy, gz, inv_max, D, H, W, tx, ty, tz, sh);
 
 #pragma unroll 2
     for (int e = threadIdx.x; e < kTileVox * CU; e += kRotThreads) {
@@ -147,7 +158,10 @@ rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
         vfma(acc, v5, w1.y);
         vfma(acc, v6, w1.z);
         vfma(acc, v7, w1.w);
-        dst[static_cast<long long>(o) * CU + cu] = acc;
+        if (kStream)
+            __stcs(dst + static_cast<long long>(o) * CU + cu, acc);      // written once, never re-read by this kernel
+        else
+            dst[static_cast<long long>(o) * CU + cu] = acc;
     }
 }
 
@@ -172,6 +186,8 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
                   float inv_max, const VecT* __restrict__ g_out, VecT* __restrict__ grad_in,
                   float* __restrict__ grad_aff, int CU, int D, int H, int W, int tiles_x, int tiles_y) {
     __shared__ __align__(16) RotTile s;
+    constexpr TileShape sh = tile_shape(0);
+    constexpr int kTx = sh.tx, kTy = sh.ty, kTz = sh.tz;
     __shared__ float frac[kTileVox][6];
     __shared__ float red[12][kRotThreads / 32];
     const int m = blockIdx.y;
@@ -196,7 +212,7 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
         return;
     }
     const bool need_aff = grad_aff != nullptr;
-    rotate_phase1(s, frac, affine, m, gx, gy, gz, inv_max, D, H, W, tx, ty, tz);
+    rotate_phase1(s, frac, affine, m, gx, gy, gz, inv_max, D, H, W, tx, ty, tz, sh);
 
     const float kx = 0.5f * static_cast<float>(W) * inv_max, ky = 0.5f * static_cast<float>(H) * inv_max,
                 kz = 0.5f * static_cast<float>(D) * inv_max;
@@ -280,17 +296,48 @@ extern "C" int forge_rotate_fwd(const float* vox_cl, const float* affine12, cons
     const char* fn = "forge_rotate_fwd";
     if (int e = rotate_check(fn, vox_cl, affine12, jobs, gx, gy, gz, grid_coord_max, M, C, D, H, W)) return e;
     if (!out_cl) return fail(fn, "null pointer");
-    const int tiles_x = (W + kTx - 1) / kTx, tiles_y = (H + kTy - 1) / kTy, tiles_z = (D + kTz - 1) / kTz;
+    static const int shape_id = [] {        // tuning knobs (development)
+        const char* e = getenv("FORGE_K2_SHAPE");
+        return e ? atoi(e) : 0;
+    }();
+    static const bool stream_st = [] {
+        const char* e = getenv("FORGE_K2_STREAM");
+        return e ? atoi(e) != 0 : false;
+    }();
+    const TileShape sh = tile_shape(shape_id);
+    const int tiles_x = (W + sh.tx - 1) / sh.tx, tiles_y = (H + sh.ty - 1) / sh.ty, tiles_z = (D + sh.tz - 1) / sh.tz;
     dim3 grid(tiles_x * tiles_y * tiles_z, M);
     const float inv_max = 1.0f / grid_coord_max;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (C % 4 == 0 && aligned16(vox_cl) && aligned16(out_cl)) {
-        rotate_fwd_kernel<float4><<<grid, kRotThreads, 0, st>>>(reinterpret_cast<const float4*>(vox_cl), affine12, jobs,
-                                                               gx, gy, gz, inv_max, reinterpret_cast<float4*>(out_cl),
-                                                               C / 4, D, H, W, tiles_x, tiles_y);
+        const float4* in4 = reinterpret_cast<const float4*>(vox_cl);
+        float4* out4 = reinterpret_cast<float4*>(out_cl);
+#define FORGE_K2_LAUNCH(SHAPE, STREAM)                                                                                  \
+    rotate_fwd_kernel<float4, SHAPE, STREAM><<<grid, kRotThreads, 0, st>>>(in4, affine12, jobs, gx, gy, gz, inv_max, out4, \
+                                                                          C / 4, D, H, W, tiles_x, tiles_y)
+        if (stream_st) {
+            switch (shape_id) {
+                case 1: FORGE_K2_LAUNCH(1, true); break;
+                case 2: FORGE_K2_LAUNCH(2, true); break;
+                case 3: FORGE_K2_LAUNCH(3, true); break;
+                case 4: FORGE_K2_LAUNCH(4, true); break;
+                default: FORGE_K2_LAUNCH(0, true); break;
+            }
+        } else {
+            switch (shape_id) {
+                case 1: FORGE_K2_LAUNCH(1, false); break;
+                case 2: FORGE_K2_LAUNCH(2, false); break;
+                case 3: FORGE_K2_LAUNCH(3, false); break;
+                case 4: FORGE_K2_LAUNCH(4, false); break;
+                default: FORGE_K2_LAUNCH(0, false); break;
+            }
+        }
+#undef FORGE_K2_LAUNCH
     } else {
-        rotate_fwd_kernel<float><<<grid, kRotThreads, 0, st>>>(vox_cl, affine12, jobs, gx, gy, gz, inv_max, out_cl, C, D,
-                                                              H, W, tiles_x, tiles_y);
+        const TileShape s0 = tile_shape(0);
+        const int tx0 = (W + s0.tx - 1) / s0.tx, ty0 = (H + s0.ty - 1) / s0.ty, tz0 = (D + s0.tz - 1) / s0.tz;
+        rotate_fwd_kernel<float, 0, false><<<dim3(tx0 * ty0 * tz0, M), kRotThreads, 0, st>>>(
+            vox_cl, affine12, jobs, gx, gy, gz, inv_max, out_cl, C, D, H, W, tx0, ty0);
     }
     return check_launch(fn);
 }
@@ -304,7 +351,8 @@ extern "C" int forge_rotate_bwd(const float* vox_cl, const float* affine12, cons
     if (int e = rotate_check(fn, vox_cl, affine12, jobs, gx, gy, gz, grid_coord_max, M, C, D, H, W)) return e;
     if (!g_out_cl) return fail(fn, "null pointer");
     if (!grad_vox_cl && !grad_affine12) return 0;
-    const int tiles_x = (W + kTx - 1) / kTx, tiles_y = (H + kTy - 1) / kTy, tiles_z = (D + kTz - 1) / kTz;
+    const TileShape sh = tile_shape(0);
+    const int tiles_x = (W + sh.tx - 1) / sh.tx, tiles_y = (H + sh.ty - 1) / sh.ty, tiles_z = (D + sh.tz - 1) / sh.tz;
     dim3 grid(tiles_x * tiles_y * tiles_z, M);
     const float inv_max = 1.0f / grid_coord_max;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

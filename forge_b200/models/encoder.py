@@ -43,6 +43,10 @@ class Encoder3D(nn.Module):
             nn.LeakyReLU(inplace=True),
         )
         self.fusion_feature = ConvGRU_3D(config, n_layers=1, input_size=128, hidden_size=128)
+        # arithmetic of the 3-D conv stack (fusion + heads), the FLOP-dominant part of a step:
+        # None = fp32 like the reference (cuDNN may use TF32, torch's default); torch.bfloat16 = autocast on the
+        # tensor cores (measured fuse+heads fwd+bwd, b=1: 12.7 ms -> 8.8 ms with channels-last weights)
+        self.compute_dtype = None
 
     def get_feat3D(self, img):
         z_2d = self.feature_extraction(img)
@@ -50,15 +54,28 @@ class Encoder3D(nn.Module):
         z_3d = z_2d.view(-1, 64, 32, H, W)            # the lift is a reshape: 2048 = 64 ch x 32 depth
         return self.conv1(z_3d)
 
+    def _amp(self):
+        return torch.autocast('cuda', dtype=self.compute_dtype, enabled=self.compute_dtype is not None)
+
+    def channels_last_3d_(self):
+        """Convert the 3-D conv weights to channels_last_3d in place (what cuDNN's tensor-core kernels want;
+        K2 already emits channels-last volumes).  state_dict keys / values are unaffected."""
+        for mod in (self.fusion_feature, self.features_head, self.density_head, self.conv1):
+            mod.to(memory_format=torch.channels_last_3d)
+        return self
+
     def get_density3D(self, z_3d):
-        return self.density_head(z_3d)
+        with self._amp():
+            return self.density_head(z_3d).float()
 
     def get_render_features(self, x):
-        return self.features_head(x)
+        with self._amp():
+            return self.features_head(x).float()
 
     def fuse(self, x):
         # x in [b,t,c,d,h,w]; hidden state initialised from the view mean (reference :59-63)
-        return self.fusion_feature(x, [self.fusion_feature.fusion_conv(x.mean(dim=1))])
+        with self._amp():
+            return self.fusion_feature(x, [self.fusion_feature.fusion_conv(x.mean(dim=1))]).float()
 
     def forward(self, x):
         raise NotImplementedError

@@ -106,7 +106,11 @@ def main():
 
     results = {}
     arms = [("forge_b200", step_forge)] + ([] if args.no_ref else [("reference op sequence (oracle on GPU)", step_ref)])
+    arms.append(("forge_b200, bf16 fusion+heads (channels-last weights)", step_forge))
     for name, fn in arms:
+        if "bf16" in name:
+            model.encoder_3d.channels_last_3d_()
+            model.encoder_3d.compute_dtype = torch.bfloat16
         q, t = make_params()
         opt = torch.optim.Adam([q, t], lr=1e-3)
         for _ in range(3):
