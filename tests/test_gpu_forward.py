@@ -366,3 +366,60 @@ def test_rotate_cfg4_stress_vs_oracle():
     outside = out2[:, 1:].abs().max().item()
     assert passthrough
     assert outside == 0.0
+
+
+def test_raymarch_non_cubic_volume_and_single_sample():
+    """D != H != W volumes (x<->W, y<->H, z<->D axis order) and the P = 1 edge case."""
+    torch.manual_seed(5)
+    D, H, W, S = 10, 12, 14, 24
+    feat = torch.randn(2, 16, D, H, W)
+    dens = torch.rand(2, 1, D, H, W) * 0.5
+    R, T, _ = syn.ring_cameras(4, seed=9)
+    K = syn.intrinsics(4, 2 * S)
+    v2v = torch.tensor([0, 1, 1, 0], dtype=torch.int32)
+    for P in (17, 1):
+        m = VolRender(syn.make_config(img_size=2 * S, n_pts_per_ray=P, min_depth=0.9 if P == 1 else 0.5,
+                                      max_depth=1.4 if P == 1 else 2.0)).to(DEV).eval()
+        with torch.no_grad():
+            f, s, d, _, _, Kh = m.render_features(dict(R=R.clone(), T=T.clone(), K=K.clone()), feat.to(DEV), dens.to(DEV),
+                                                  True, view2vol=v2v)
+            fo, so, do = cf.raymarch(R, T, Kh.cpu(), feat[v2v.long()], dens[v2v.long()], S, P, m.min_depth, m.max_depth, 1.0)
+        assert (f.cpu() - fo).abs().max().item() <= TOL and (s.cpu() - so).abs().max().item() <= TOL
+        assert (d.cpu() - do).abs().max().item() <= TOL
+        assert s.abs().max().item() > 0.01
+
+
+def test_raymarch_omniobject3d_geometry_and_density_clamp():
+    """omniobject3d config: volume_size 2.0, depths 3..5, camera at 4.0, densities clamped to [0,1] by the model
+    (reference config/omniobject3d, models/model.py:140-141)."""
+    img, vol, P = 64, 16, 32
+    inp = syn.render_inputs(1, 3, img, vol, seed=21, dense=True)
+    Rs, Ts, _ = syn.ring_cameras(3, camera_z=4.0, seed=2)
+    cfg = syn.make_config(img_size=img, n_pts_per_ray=P, min_depth=3.0, max_depth=5.0, volume_size=2.0, camera_z=4.0,
+                          dataset_name='omniobject3d')
+    m = VolRender(cfg).to(DEV).eval()
+    dens = inp['dens'].clamp(min=0.0, max=1.0)
+    with torch.no_grad():
+        f, s, d, _, _, Kh = m.render_features(dict(R=Rs.clone(), T=Ts.clone(), K=inp['K'].clone()), inp['feat'].to(DEV),
+                                              dens.to(DEV), True, view2vol=inp['view2vol'])
+        fo, so, do = cf.raymarch(Rs, Ts, Kh.cpu(), inp['feat'].expand(3, -1, -1, -1, -1), dens.expand(3, -1, -1, -1, -1),
+                                 img // 2, P, 3.0, 5.0, 2.0)
+    assert (f.cpu() - fo).abs().max().item() <= TOL and (s.cpu() - so).abs().max().item() <= TOL
+    assert (d.cpu() - do).abs().max().item() <= 5 * TOL          # depths are ~4: same relative accuracy
+    assert 0.2 < s.max().item() <= 1.0 + 1e-6
+
+
+def test_rotate_non_cubic_volume():
+    vox = torch.randn(1, 3, 8, 6, 10, 12)
+    _, poses = syn.rotate_inputs(1, 3, 1, 4, seed=3)
+    m = Rotate_world(syn.make_config()).to(DEV)
+    with torch.no_grad():
+        out = m(vox.to(DEV), poses.to(DEV), grid_size=12)
+    gx, gmax = cf.rotate_axis(12, 1.0)
+    A = cf.rotate_affine(poses)
+    gz, gy = cf.rotate_axis(6, 1.0)[0], cf.rotate_axis(10, 1.0)[0]
+    Z, Y, X = torch.meshgrid(gz, gy, gx, indexing='ij')
+    Pm = torch.stack([X, Y, Z, torch.ones_like(X)], dim=-1)
+    grid = torch.einsum('mab,dhwb->mdhwa', A[:, :3, :], Pm) / gmax
+    ref = torch.nn.functional.grid_sample(vox[0, 1:], grid, mode='bilinear', padding_mode='zeros', align_corners=False)
+    assert (out[0, 1:].cpu() - ref).abs().max().item() <= TOL
