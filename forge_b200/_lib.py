@@ -48,10 +48,10 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.LIB
-        if not os.path.exists(path):
-            try:
-                path = _build.build()
-            except Exception as e:  # no silent fallback
+        try:
+            path = _build.build()       # no-op when the library matches the sources (digest stamp)
+        except Exception as e:
+            if not os.path.exists(path):  # no silent fallback
                 raise RuntimeError(
                     "forge_b200: libforge_b200.so is missing and could not be built (%s). "
                     "The CUDA extension is mandatory; there is no CPU path." % e) from e
