@@ -15,33 +15,22 @@ import torchvision
 from .fusion import ConvGRU_3D
 
 
+def _upsample_stem():
+    """128 -> 32 channels, x2 resolution (shared shape of both heads)"""
+    return [nn.ConvTranspose3d(128, 32, 4, stride=2, padding=1), nn.BatchNorm3d(32), nn.LeakyReLU(inplace=True)]
+
+
 class Encoder3D(nn.Module):
     def __init__(self, config):
         super(Encoder3D, self).__init__()
         self.feature_extraction = get_resnet50()
-
-        self.features_head = nn.Sequential(
-            nn.ConvTranspose3d(128, 32, 4, stride=2, padding=1),
-            nn.BatchNorm3d(32),
-            nn.LeakyReLU(inplace=True),
-            nn.Conv3d(32, 16, 3, padding=1),
-            nn.BatchNorm3d(16),
-        )
-        self.density_head = nn.Sequential(
-            nn.ConvTranspose3d(128, 32, 4, stride=2, padding=1),
-            nn.BatchNorm3d(32),
-            nn.LeakyReLU(inplace=True),
-            nn.Conv3d(32, 8, 3, padding=1),
-            nn.BatchNorm3d(8),
-            nn.LeakyReLU(inplace=True),
-            nn.Conv3d(8, 1, 3, padding=1),
-            nn.ReLU(inplace=True),
-        )
-        self.conv1 = nn.Sequential(
-            nn.Conv3d(64, 128, 3, padding=1),
-            nn.BatchNorm3d(128),
-            nn.LeakyReLU(inplace=True),
-        )
+        # 16-channel render features: indices 0,1,3,4 carry parameters (reference :16-22)
+        self.features_head = nn.Sequential(*_upsample_stem(), nn.Conv3d(32, 16, 3, padding=1), nn.BatchNorm3d(16))
+        # non-negative density: indices 0,1,3,4,6 carry parameters (reference :25-34)
+        self.density_head = nn.Sequential(*_upsample_stem(), nn.Conv3d(32, 8, 3, padding=1), nn.BatchNorm3d(8),
+                                          nn.LeakyReLU(inplace=True), nn.Conv3d(8, 1, 3, padding=1), nn.ReLU(inplace=True))
+        # first 3-D conv after the reshape-lift (reference :36-40)
+        self.conv1 = nn.Sequential(nn.Conv3d(64, 128, 3, padding=1), nn.BatchNorm3d(128), nn.LeakyReLU(inplace=True))
         self.fusion_feature = ConvGRU_3D(config, n_layers=1, input_size=128, hidden_size=128)
         # arithmetic of the 3-D conv stack (fusion + heads), the FLOP-dominant part of a step (SURVEY 8f.3):
         # None = fp32 like the reference (cuDNN may use TF32, torch's default); torch.bfloat16 = autocast on the

@@ -10,60 +10,47 @@ import torch
 import torch.nn as nn
 
 
+def _conv_bn_act(cin, cout):
+    return [nn.Conv3d(cin, cout, 3, padding=1), nn.BatchNorm3d(cout), nn.LeakyReLU(inplace=True)]
+
+
 class ConvGRUCell_3D(nn.Module):
-    """h' = (1 - u) h + u tanh(W_o [x, r h]),  (u, r) = sigmoid(W_g [x, h])   (reference :21-35)"""
+    """(u, r) = sigmoid(W_g * [x, h]);  c = tanh(W_o * [x, r h]);  h' = h + u (c - h)   (reference :21-35)"""
 
     def __init__(self, config, input_size, hidden_size):
         super().__init__()
-        self.input_size = input_size
-        self.hidden_size = hidden_size
-        self.conv_gate = nn.Conv3d(input_size + hidden_size, 2 * hidden_size, 3, padding=1)
-        self.out_gate = nn.Conv3d(input_size + hidden_size, hidden_size, 3, padding=1)
+        self.input_size, self.hidden_size = input_size, hidden_size
+        width = input_size + hidden_size
+        self.conv_gate = nn.Conv3d(width, 2 * hidden_size, 3, padding=1)     # update | reset
+        self.out_gate = nn.Conv3d(width, hidden_size, 3, padding=1)          # candidate state
 
     def forward(self, x, prev_state=None):
-        if prev_state is None:
-            b, _, d, h, w = x.shape
-            prev_state = x.new_zeros(b, self.hidden_size, d, h, w)
-        gates = self.conv_gate(torch.cat([x, prev_state], dim=1))
-        update, reset = torch.split(gates, self.hidden_size, dim=1)
-        update, reset = torch.sigmoid(update), torch.sigmoid(reset)
-        candidate = torch.tanh(self.out_gate(torch.cat([x, prev_state * reset], dim=1)))
-        return prev_state * (1 - update) + candidate * update
+        h = prev_state
+        if h is None:
+            h = x.new_zeros((x.shape[0], self.hidden_size) + tuple(x.shape[2:]))
+        u, r = torch.sigmoid(self.conv_gate(torch.cat((x, h), 1))).split(self.hidden_size, dim=1)
+        c = torch.tanh(self.out_gate(torch.cat((x, h * r), 1)))
+        return h * (1 - u) + c * u
 
 
 class ConvGRU_3D(nn.Module):
     def __init__(self, config, n_layers=1, input_size=16, hidden_size=16):
         super(ConvGRU_3D, self).__init__()
-        self.input_size = input_size
-        self.hidden_size = hidden_size
-        self.n_layers = n_layers
-        self.cells = nn.ModuleList(
-            [ConvGRUCell_3D(config, input_size if i == 0 else hidden_size, hidden_size) for i in range(n_layers)])
+        self.input_size, self.hidden_size, self.n_layers = input_size, hidden_size, n_layers
+        widths = [input_size] + [hidden_size] * (n_layers - 1)
+        self.cells = nn.ModuleList(ConvGRUCell_3D(config, w, hidden_size) for w in widths)
         self.fusion_norm = nn.BatchNorm3d(hidden_size)
-        self.fusion_conv = nn.Sequential(
-            nn.Conv3d(input_size, input_size, 3, padding=1),
-            nn.BatchNorm3d(input_size),
-            nn.LeakyReLU(inplace=True),
-            nn.Conv3d(input_size, input_size, 3, padding=1),
-            nn.BatchNorm3d(input_size),
-            nn.LeakyReLU(inplace=True),
-        )
+        self.fusion_conv = nn.Sequential(*_conv_bn_act(input_size, input_size), *_conv_bn_act(input_size, input_size))
 
     def forward(self, x, hidden=None):
-        '''
-        x: [b,t,c,d,h,w]; hidden: optional list with one initial state per layer
-        '''
-        seq_len = x.shape[1]
-        if not hidden:
-            hidden = [None] * self.n_layers
-        layer_input = x
+        """x [b,t,c,d,h,w] (view sequence); hidden: optional list of initial states, one per layer -> fusion_norm(h_T)"""
+        states = list(hidden) if hidden else [None] * self.n_layers
+        seq = x.unbind(dim=1)
         h = None
-        for layer_idx, cell in enumerate(self.cells):
-            h = hidden[layer_idx]
-            outputs = []
-            for t in range(seq_len):
-                h = cell(layer_input[:, t], h)
-                outputs.append(h)
-            if layer_idx + 1 < self.n_layers:
-                layer_input = torch.stack(outputs, dim=1)
+        for cell, h in zip(self.cells, states):
+            outs = []
+            for x_t in seq:
+                h = cell(x_t, h)
+                outs.append(h)
+            seq = outs                       # the next layer consumes this layer's state sequence
         return self.fusion_norm(h)
