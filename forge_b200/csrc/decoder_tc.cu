@@ -1,0 +1,427 @@
+// Tensor-core decoder: relu(conv_rgb(x)) of reference models/volume_render.py:29-37,73 with bf16
+// operands / fp32 accumulation on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM)
+// -- the "bf16 decoder" of BASELINE.json configs[2].  Inference only (BatchNorm in eval mode).
+//
+// Every layer is an implicit GEMM with NO im2col: activations sit in shared memory as
+//   plane[c / 8][pixel][c % 8]   (bf16: one pixel of one plane = 16 bytes, pixels row-major, pitch P)
+// which is exactly the un-swizzled K-major "core matrix" layout of a UMMA operand: 8 consecutive
+// pixels x 8 channels = one 8x16-byte core matrix, SBO (next 8 rows) = 128 B, LBO (next 8 values
+// of K) = the plane stride.  Row m of the A operand is the pixel with flattened index m, so a
+// filter tap (ky, kx) is the SAME descriptor with its start address advanced by (ky*P + kx)*16 B:
+// one tcgen05.mma (M=128 pixels, N=16 output channels, K=16) per tap and 128 flattened pixels.
+// Flattened pixels that fall in the halo columns compute garbage that is never read back.
+//
+//   layer 1  ConvTranspose2d(16->16, k6, s2, p2) = four 3x3 convolutions (one per output parity
+//            class), K = 16 input channels per tap: 4 classes x 3 M-tiles x 9 taps
+//   layer 2  Conv2d(16->8, k5): 7 M-tiles x 25 taps (N padded 8 -> 16)
+//   layer 3  Conv2d(8->3, k5): the input has ONE 8-channel plane, so K = 16 covers TWO taps whose
+//            distance is put into LBO (640 B = one row down, or 16 B = one pixel right):
+//            5 M-tiles x 13 MMAs (N padded 3 -> 16)
+//
+// Epilogues (tcgen05.ld, one accumulator row per thread) apply scale/shift (folded BN + bias),
+// LeakyReLU, the zero padding of the next convolution, and write bf16 planes for the next layer;
+// the last one applies ReLU and stores fp32 NCHW.  Weights (37 KB of prebuilt B tiles) arrive by
+// one bulk async copy (TMA engine).  Persistent CTAs, 2 per SM (100 KB smem, 256 TMEM columns).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace forge {
+namespace dtc {
+
+constexpr int kThreads = 256;
+constexpr int TOX = 32, TOY = 16;                 // output tile
+constexpr int IN_W = TOX / 2 + 6, IN_H = TOY / 2 + 6;     // 22 x 14 input pixels
+constexpr int L1_W = TOX + 8, L1_H = TOY + 8;             // 40 x 24 layer-1 pixels; 40 is also the layer-2 pitch
+constexpr int M1_TILES = 3, M2_TILES = 7, M3_TILES = 5;   // 128-row tiles of flattened pixels per layer
+constexpr int IN_PLANE = 432;                     // >= 3*128 + 2*22 + 2
+constexpr int L1_PLANE = 1064;                    // >= 7*128 + 4*40 + 4
+constexpr int L2_PLANE = 896;                     // = 7*128 >= 5*128 + 4*40 + 5
+static_assert(IN_PLANE >= M1_TILES * 128 + 2 * IN_W + 2, "input plane too small for the flattened over-read");
+static_assert(L1_PLANE >= M2_TILES * 128 + 4 * L1_W + 4, "layer-1 plane too small");
+static_assert(L2_PLANE >= M3_TILES * 128 + 4 * L1_W + 5 && L2_PLANE >= M2_TILES * 128, "layer-2 plane too small");
+static_assert((TOY / 2 + 4) * IN_W <= M1_TILES * 128 && (TOY + 4) * L1_W <= M2_TILES * 128 && TOY * L1_W <= M3_TILES * 128,
+              "M tiles do not cover the layer");
+
+constexpr int BTILE = 512;                        // one B tile: [k/8][n = 16][k%8] bf16
+constexpr int W1_OFF = 0, W2_OFF = W1_OFF + 36 * BTILE, W3_OFF = W2_OFF + 25 * BTILE, PRM_OFF = W3_OFF + 13 * BTILE;
+constexpr int WPACK_BYTES = PRM_OFF + 256;        // 38144
+constexpr int SM_W = 0, SM_IN = SM_W + WPACK_BYTES, SM_L1 = SM_IN + 2 * IN_PLANE * 16, SM_L2 = SM_L1 + 2 * L1_PLANE * 16,
+              SM_BAR = SM_L2 + L2_PLANE * 16, SM_TOTAL = SM_BAR + 32;
+constexpr int TMEM_COLS = 256;                    // 12 accumulators x 16 columns in layer 1
+
+// instruction descriptor (PTX ISA "Instruction descriptor", kind::f16): D = f32, A = B = bf16, both K-major,
+// N = 16, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// shared-memory matrix descriptor, no swizzle: start address, leading (K) and stride (M/N) byte offsets
+// in 16-byte units, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return static_cast<uint64_t>((saddr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spins = 0; !done; ++spins) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (spins > (1 << 22)) __trap();          // a lost completion must fail loudly, not hang the GPU
+    }
+    __syncwarp();                                 // the tcgen05.ld that follows is .sync.aligned
+}
+__device__ __forceinline__ void bulk_load_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : 0.01f * v; }
+
+__global__ void __launch_bounds__(kThreads, 2)
+decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__ wpack, float* __restrict__ rgb, int Sh,
+                  int Sw, int tiles_x, int tiles_y, int total_tiles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sW = smem + SM_W;
+    unsigned char* sIn = smem + SM_IN;
+    unsigned char* sL1 = smem + SM_L1;
+    unsigned char* sL2 = smem + SM_L2;
+    unsigned long long* wbar = reinterpret_cast<unsigned long long*>(smem + SM_BAR);
+    unsigned long long* mbar = wbar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16);
+    const float* prm = reinterpret_cast<const float*>(sW + PRM_OFF);      // s1[16] b1[16] s2[8] b2[8] b3[4]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int OH = 2 * Sh, OW = 2 * Sw;
+
+    // ---- one-time setup: barriers, weights (bulk async copy), TMEM, zeroed activation planes ----
+    if (tid == 0) {
+        mbar_init(wbar, 1);
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) bulk_load_g2s(sW, wpack, WPACK_BYTES, wbar);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int e = tid; e < (SM_BAR - SM_IN) / 16; e += kThreads)          // pads must hold finite values
+        reinterpret_cast<uint4*>(sIn)[e] = make_uint4(0u, 0u, 0u, 0u);
+    mbar_wait(wbar, 0);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);   // this warp's TMEM lane quarter
+    const int row = (warp & 3) * 32 + lane, grp = warp >> 2;             // accumulator row of this thread, warp group
+    const uint32_t aIn = smem_u32(sIn), aL1 = smem_u32(sL1), aL2 = smem_u32(sL2), aW = smem_u32(sW);
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n = tile / (tiles_x * tiles_y), t2 = tile - n * tiles_x * tiles_y;
+        const int tyi = t2 / tiles_x, txi = t2 - tyi * tiles_x;
+        const int Y0 = tyi * TOY, X0 = txi * TOX;
+
+        // ---- P0: input tile fp32 NHWC -> two bf16 planes (zeros outside the image) ----
+        {
+            const int iy0 = Y0 / 2 - 3, ix0 = X0 / 2 - 3;
+            const float4* xin = reinterpret_cast<const float4*>(x) + static_cast<long long>(n) * Sh * Sw * 4;
+            for (int e = tid; e < IN_H * IN_W * 2; e += kThreads) {
+                const int px = e >> 1, half = e & 1;
+                const int r = px / IN_W, c = px - r * IN_W;
+                const int iy = iy0 + r, ix = ix0 + c;
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (iy >= 0 && iy < Sh && ix >= 0 && ix < Sw) {
+                    const float4* p = xin + (static_cast<long long>(iy) * Sw + ix) * 4 + half * 2;
+                    v0 = __ldg(p);
+                    v1 = __ldg(p + 1);
+                }
+                *reinterpret_cast<uint4*>(sIn + (half * IN_PLANE + px) * 16) =
+                    make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+            }
+        }
+        proxy_fence();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- P1: transposed conv as 4 parity classes x 3 M-tiles x 9 taps ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int cls = 0; cls < 4; ++cls)
+#pragma unroll 1
+                for (int j = 0; j < M1_TILES; ++j) {
+                    const uint32_t d = tmem + (cls * M1_TILES + j) * 16;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int a = t / 3, b = t - a * 3;       // source pixel offset (rows, cols) inside the input tile
+                        umma_bf16(d, make_desc(aIn + (j * 128 + a * IN_W + b) * 16, IN_PLANE * 16, 128),
+                                  make_desc(aW + W1_OFF + (cls * 9 + t) * BTILE, 256, 128), IDESC, t > 0);
+                    }
+                }
+            umma_commit(mbar);
+        }
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < 6; ++i) {
+            const int ai = 2 * i + grp, cls = ai / M1_TILES, j = ai - cls * M1_TILES, py = cls >> 1, px = cls & 1;
+            float acc[16];
+            tmem_ld16(t_lane + ai * 16, acc);
+            const int m = j * 128 + row, yr = m / IN_W, xr = m - yr * IN_W;
+            if (yr < TOY / 2 + 4 && xr < TOX / 2 + 4) {
+                const int lr = 2 * yr + py, lc = 2 * xr + px, oy = Y0 - 4 + lr, ox = X0 - 4 + lc;
+                const bool inside = oy >= 0 && oy < OH && ox >= 0 && ox < OW;     // zero padding of layer 2
+                uint32_t q[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float v0 = inside ? lrelu(fmaf(acc[2 * c], prm[2 * c], prm[16 + 2 * c])) : 0.f;
+                    const float v1 = inside ? lrelu(fmaf(acc[2 * c + 1], prm[2 * c + 1], prm[16 + 2 * c + 1])) : 0.f;
+                    q[c] = pack_bf16(v0, v1);
+                }
+                const int idx = lr * L1_W + lc;
+                *reinterpret_cast<uint4*>(sL1 + idx * 16) = make_uint4(q[0], q[1], q[2], q[3]);
+                *reinterpret_cast<uint4*>(sL1 + (L1_PLANE + idx) * 16) = make_uint4(q[4], q[5], q[6], q[7]);
+            }
+        }
+        proxy_fence();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- P2: conv 5x5 16 -> 8: 7 M-tiles x 25 taps ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int j = 0; j < M2_TILES; ++j) {
+                const uint32_t d = tmem + j * 16;
+#pragma unroll
+                for (int t = 0; t < 25; ++t) {
+                    const int ky = t / 5, kx = t - ky * 5;
+                    umma_bf16(d, make_desc(aL1 + (j * 128 + ky * L1_W + kx) * 16, L1_PLANE * 16, 128),
+                              make_desc(aW + W2_OFF + t * BTILE, 256, 128), IDESC, t > 0);
+                }
+            }
+            umma_commit(mbar);
+        }
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            const int j = 2 * i + grp;
+            if (j < M2_TILES) {                                   // warp-uniform
+                float acc[8];
+                tmem_ld8(t_lane + j * 16, acc);
+                const int m = j * 128 + row, yr = m / L1_W, xr = m - yr * L1_W;
+                const int oy = Y0 - 2 + yr, ox = X0 - 2 + xr;
+                const bool inside = oy >= 0 && oy < OH && ox >= 0 && ox < OW;     // zero padding of layer 3
+                uint32_t q[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float v0 = inside ? lrelu(fmaf(acc[2 * c], prm[32 + 2 * c], prm[40 + 2 * c])) : 0.f;
+                    const float v1 = inside ? lrelu(fmaf(acc[2 * c + 1], prm[32 + 2 * c + 1], prm[40 + 2 * c + 1])) : 0.f;
+                    q[c] = pack_bf16(v0, v1);
+                }
+                *reinterpret_cast<uint4*>(sL2 + m * 16) = make_uint4(q[0], q[1], q[2], q[3]);
+            }
+        }
+        proxy_fence();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- P3: conv 5x5 8 -> 3: two taps per MMA (LBO = their distance), 5 M-tiles x 13 ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int j = 0; j < M3_TILES; ++j) {
+                const uint32_t d = tmem + j * 16;
+#pragma unroll
+                for (int q = 0; q < 13; ++q) {
+                    // q < 10: taps (ky, kx) and (ky + 1, kx), ky = 2 (q / 5), kx = q % 5; q >= 10: taps (4, kx), (4, kx + 1), kx = 2 (q - 10)
+                    const int shift = q < 10 ? (2 * (q / 5)) * L1_W + (q % 5) : 4 * L1_W + 2 * (q - 10);
+                    const int lbo = q < 10 ? L1_W * 16 : 16;
+                    umma_bf16(d, make_desc(aL2 + (j * 128 + shift) * 16, lbo, 128),
+                              make_desc(aW + W3_OFF + q * BTILE, 256, 128), IDESC, q > 0);
+                }
+            }
+            umma_commit(mbar);
+        }
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) {
+            const int j = 2 * i + grp;
+            if (j < M3_TILES) {
+                float acc[4];
+                tmem_ld4(t_lane + j * 16, acc);
+                const int m = j * 128 + row, yr = m / L1_W, xr = m - yr * L1_W;
+                const int oy = Y0 + yr, ox = X0 + xr;
+                if (yr < TOY && xr < TOX && oy < OH && ox < OW) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        rgb[((static_cast<long long>(n) * 3 + c) * OH + oy) * OW + ox] = fmaxf(acc[c] + prm[48 + c], 0.f);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// Test hook kernel: ONE tcgen05.mma (M=128, N=16, K=16, bf16) over a caller-provided shared-memory image with
+// caller-provided descriptor fields; D [128][16] fp32 comes back through tcgen05.ld.
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const unsigned char* __restrict__ image, int image_bytes, unsigned a_off, unsigned a_lbo, unsigned a_sbo,
+                  unsigned b_off, unsigned b_lbo, unsigned b_sbo, float* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < image_bytes / 16; e += 128) reinterpret_cast<uint4*>(smem)[e] = reinterpret_cast<const uint4*>(image)[e];
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (tid == 0) {
+        umma_bf16(tmem, make_desc(smem_u32(smem) + a_off, a_lbo, a_sbo), make_desc(smem_u32(smem) + b_off, b_lbo, b_sbo), IDESC, 0);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    float acc[16];
+    tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16), acc);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) out[(warp * 32 + lane) * 16 + c] = acc[c];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32) : "memory");
+    }
+}
+
+}  // namespace dtc
+}  // namespace forge
+
+extern "C" int forge_decoder_tc_wpack_bytes(void) { return forge::dtc::WPACK_BYTES; }
+
+extern "C" int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, float* rgb_nchw, int N, int S_h, int S_w,
+                                    int max_ctas, void* stream) {
+    using namespace forge;
+    using namespace forge::dtc;
+    const char* fn = "forge_decoder_tc_fwd";
+    if (!x_nhwc || !wpack || !rgb_nchw) return fail(fn, "null pointer");
+    if (N <= 0 || S_h <= 0 || S_w <= 0) return fail(fn, "non-positive size");
+    if (!aligned16(x_nhwc) || !aligned16(wpack)) return fail(fn, "x_nhwc / wpack must be 16-byte aligned");
+    const int tiles_x = (2 * S_w + TOX - 1) / TOX, tiles_y = (2 * S_h + TOY - 1) / TOY;
+    const long long total = static_cast<long long>(N) * tiles_x * tiles_y;
+    if (total > 0x7fffffffLL) return fail(fn, "too many tiles for one launch");
+    static thread_local int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(decoder_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        if (e != cudaSuccess) {
+            sm_count = 0;
+            return fail(fn, std::string("device setup: ") + cudaGetErrorString(e));
+        }
+    }
+    int ctas = 2 * sm_count;                       // persistent: two resident CTAs per SM
+    if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+    if (total < ctas) ctas = static_cast<int>(total);
+    decoder_tc_kernel<<<ctas, kThreads, SM_TOTAL, static_cast<cudaStream_t>(stream)>>>(
+        x_nhwc, static_cast<const unsigned char*>(wpack), rgb_nchw, S_h, S_w, tiles_x, tiles_y, static_cast<int>(total));
+    return check_launch(fn);
+}
+
+extern "C" int forge_umma_probe(const void* image, int image_bytes, unsigned a_off, unsigned a_lbo, unsigned a_sbo,
+                                unsigned b_off, unsigned b_lbo, unsigned b_sbo, float* out, void* stream) {
+    using namespace forge;
+    using namespace forge::dtc;
+    const char* fn = "forge_umma_probe";
+    if (!image || !out) return fail(fn, "null pointer");
+    if (image_bytes <= 0 || image_bytes % 16 || image_bytes > 200 * 1024) return fail(fn, "image_bytes must be a multiple of 16, <= 200 KiB");
+    if ((a_off | a_lbo | a_sbo | b_off | b_lbo | b_sbo) & 15u) return fail(fn, "offsets must be multiples of 16 bytes");
+    cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, image_bytes);
+    if (e != cudaSuccess) return fail(fn, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    umma_probe_kernel<<<1, 128, image_bytes, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const unsigned char*>(image), image_bytes, a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo, out);
+    return check_launch(fn);
+}

@@ -68,8 +68,9 @@ class VolRender(nn.Module):
             nn.Conv2d(8, 3, kernel_size=self.k_size, stride=1, padding=self.pad_size),
         )
         self._zs = {}
-        # decoder arithmetic: None = fp32 like the reference; torch.bfloat16 runs conv_rgb under autocast on
-        # the tensor cores (BASELINE.json configs[2] "bf16 decoder"; RGB then deviates ~1e-2, not 1e-4)
+        # decoder arithmetic: None = fp32 like the reference; torch.bfloat16 = bf16 operands / fp32 accumulation on
+        # the tensor cores (BASELINE.json configs[2] "bf16 decoder"; RGB then deviates ~1e-2, not 1e-4): the
+        # tcgen05 kernel in eval mode, cuDNN under autocast in training mode
         self.decoder_dtype = None
         self.fused_decoder = True
         self._wpack = None
@@ -147,21 +148,26 @@ class VolRender(nn.Module):
             else:
                 return rendered_imgs, rendered_silhouettes
 
-    def _decoder_pack(self, device):
-        """BN-folded weight pack for the fused decoder, rebuilt only when a parameter / buffer changed."""
+    def _decoder_pack(self, device, tc=False):
+        """Weight pack for the fused decoder (fp32, BN folded) or the tensor-core decoder (bf16 B tiles),
+        rebuilt only when a parameter / buffer changed."""
         tensors = list(self.conv_rgb.parameters()) + list(self.conv_rgb.buffers())
-        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+        key = (str(device), tc) + tuple((t.data_ptr(), t._version) for t in tensors)
         if self._wpack is None or self._wpack[0] != key:
-            self._wpack = (key, ops.pack_decoder_weights(self.conv_rgb))
+            pack = ops.pack_decoder_tc_weights if tc else ops.pack_decoder_weights
+            self._wpack = (key, pack(self.conv_rgb))
         return self._wpack[1]
 
     def decode(self, feat_nhwc):
         """[N,S,S,16] composited features -> relu(conv_rgb(.)) [N,3,2S,2S] (reference :73).
-        eval mode, fp32, k_size 5: one fused kernel; training mode (batch-statistics BN) or a
+        eval mode, k_size 5: one fused kernel -- fp32 FFMA (decoder_dtype None, the 1e-4 parity path) or bf16
+        tcgen05 tensor cores (decoder_dtype torch.bfloat16); training mode (batch-statistics BN) or a
         non-default decoder: the module's own cuDNN convs on the NHWC buffer."""
-        if (self.fused_decoder and not self.training and self.decoder_dtype is None and self.k_size == 5
-                and feat_nhwc.is_cuda):
+        fused = self.fused_decoder and not self.training and self.k_size == 5 and feat_nhwc.is_cuda
+        if fused and self.decoder_dtype is None:
             return ops.decoder_fused(feat_nhwc, self._decoder_pack(feat_nhwc.device), self.conv_rgb)
+        if fused and self.decoder_dtype == torch.bfloat16:        # tcgen05 implicit GEMMs (decoder_tc.cu)
+            return ops.decoder_tc(feat_nhwc, self._decoder_pack(feat_nhwc.device, tc=True), self.conv_rgb)
         x = feat_nhwc.permute(0, 3, 1, 2)                             # NCHW view of the NHWC kernel output
         if self.decoder_dtype is None:
             return F.relu(self.conv_rgb(x))

@@ -276,3 +276,96 @@ def decoder_fused(x_nhwc, wpack, conv_rgb):
     if x_nhwc.shape[-1] != 16:
         raise ValueError("the decoder input must have 16 channels")
     return _Decoder.apply(_f32c(x_nhwc), wpack, conv_rgb)
+
+
+# ---- tensor-core (bf16) decoder ------------------------------------------------------------------
+def _btile(mat):
+    """[n <= 16, k <= 16] -> one UMMA B tile [k / 8][n = 16][k % 8] (K-major core matrices, zero padded)."""
+    t = mat.new_zeros(16, 16)
+    t[:mat.shape[0], :mat.shape[1]] = mat
+    return t.view(16, 2, 8).permute(1, 0, 2).contiguous()
+
+
+def decoder_tc_taps3():
+    """The 13 tap pairs ((kyA, kxA), (kyB, kxB) | None) of layer 3, in the order decoder_tc.cu issues them."""
+    pairs = []
+    for q in range(13):
+        if q < 10:
+            ky, kx = 2 * (q // 5), q % 5
+            pairs.append(((ky, kx), (ky + 1, kx)))
+        else:
+            kx = 2 * (q - 10)
+            pairs.append(((4, kx), (4, kx + 1) if kx + 1 < 5 else None))
+    return pairs
+
+
+def pack_decoder_tc_weights(conv_rgb):
+    """Weight pack for forge_decoder_tc_fwd from the reference-shaped ``conv_rgb`` Sequential in eval mode:
+    bf16 B tiles (36 + 25 + 13 tiles of 512 B) followed by the fp32 epilogue constants
+    s1[16] b1[16] s2[8] b2[8] b3[4] (BN scale/shift with the conv bias folded in); layout in forge_b200.h."""
+    ct, bn1, _, c2, bn2, _, c3 = conv_rgb
+    with torch.no_grad():
+        wt, w2, w3 = ct.weight.float(), c2.weight.float(), c3.weight.float()
+        tiles = []
+        for py in (0, 1):
+            for px in (0, 1):
+                for a in range(3):
+                    for b in range(3):
+                        tiles.append(_btile(wt[:, :, py + 4 - 2 * a, px + 4 - 2 * b].t()))        # [co, ci]
+        for ky in range(5):
+            for kx in range(5):
+                tiles.append(_btile(w2[:, :, ky, kx]))                                          # [co 8, ci 16]
+        for ta, tb in decoder_tc_taps3():
+            m = wt.new_zeros(3, 16)
+            m[:, :8] = w3[:, :, ta[0], ta[1]]
+            if tb is not None:
+                m[:, 8:] = w3[:, :, tb[0], tb[1]]
+            tiles.append(_btile(m))
+        wb = torch.stack(tiles).to(torch.bfloat16).contiguous().view(torch.uint8).reshape(-1)
+        s1 = bn1.weight / torch.sqrt(bn1.running_var + bn1.eps)
+        s2 = bn2.weight / torch.sqrt(bn2.running_var + bn2.eps)
+        b1 = (ct.bias - bn1.running_mean) * s1 + bn1.bias
+        b2 = (c2.bias - bn2.running_mean) * s2 + bn2.bias
+        prm = torch.zeros(64, dtype=torch.float32, device=wt.device)
+        prm[0:16], prm[16:32], prm[32:40], prm[40:48], prm[48:51] = s1, b1, s2, b2, c3.bias
+        pack = torch.cat([wb, prm.view(torch.uint8).reshape(-1)]).contiguous()
+    assert pack.numel() == _lib.load().forge_decoder_tc_wpack_bytes()
+    return pack
+
+
+class _DecoderTC(torch.autograd.Function):
+    """bf16 tensor-core inference decoder; the backward pass re-runs the module's own convs (cuDNN)."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, wpack, conv_rgb, max_ctas):
+        N, Sh, Sw, _ = x_nhwc.shape
+        rgb = torch.empty(N, 3, 2 * Sh, 2 * Sw, dtype=torch.float32, device=x_nhwc.device)
+        with torch.cuda.device(x_nhwc.device):
+            _lib.call("forge_decoder_tc_fwd", _ptr(x_nhwc), _ptr(wpack), _ptr(rgb), N, Sh, Sw, int(max_ctas),
+                      _stream(x_nhwc))
+        ctx.conv_rgb = conv_rgb
+        ctx.save_for_backward(x_nhwc)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Decoder.backward(ctx, g) + (None,)
+
+
+def decoder_tc(x_nhwc, wpack, conv_rgb, max_ctas=0):
+    """x [N,S,S,16] NHWC fp32 -> relu(conv_rgb(x)) [N,3,2S,2S] fp32 on the tcgen05 tensor cores (bf16 operands,
+    fp32 accumulation, eval-mode BN)."""
+    _require_cuda(x_nhwc, wpack)
+    if x_nhwc.shape[-1] != 16:
+        raise ValueError("the decoder input must have 16 channels")
+    return _DecoderTC.apply(_f32c(x_nhwc), wpack, conv_rgb, max_ctas)
+
+
+def umma_probe(image_u8, a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo):
+    """Test hook: one tcgen05.mma (M=128, N=16, K=16, bf16, no swizzle) over a shared-memory image -> D [128,16]."""
+    _require_cuda(image_u8)
+    out = torch.empty(128, 16, dtype=torch.float32, device=image_u8.device)
+    with torch.cuda.device(image_u8.device):
+        _lib.call("forge_umma_probe", _ptr(image_u8), image_u8.numel(), a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo,
+                  _ptr(out), _stream(image_u8))
+    return out

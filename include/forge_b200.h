@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 7
+#define FORGE_ABI_VERSION 8
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -94,6 +94,30 @@ long long forge_raymarch_bwd_workspace(int N, int S_h, int S_w, int P);
 int forge_decoder_wpack_floats(void);
 int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float* rgb_nchw, int N, int S_h, int S_w,
                       void* stream);
+
+/* ---- tensor-core decoder (bf16 operands, fp32 accumulate; tcgen05.mma + TMEM) ---------------
+ * Same function as forge_decoder_fwd -- relu(conv_rgb(x)), models/volume_render.py:29-37,73, eval-mode
+ * BN -- computed as implicit GEMMs on the 5th-generation tensor cores: the "bf16 decoder" of
+ * BASELINE.json configs[2].  Inputs/outputs stay fp32 (x is rounded to bf16 on load, the two hidden
+ * activations are rounded to bf16 after BN + LeakyReLU); deviation from the fp32 module ~1e-2.
+ *   wpack (forge_decoder_tc_wpack_bytes() bytes, 16-byte aligned) =
+ *     36 + 25 + 13 B tiles of 512 B, each [k/8][n = 16][k%8] bf16 (un-swizzled K-major core matrices):
+ *       layer 1: tile[(py*2+px)*9 + a*3+b][co][ci] = Wt[ci][co][py+4-2a][px+4-2b]
+ *       layer 2: tile[ky*5+kx][co < 8][ci]          = W2[co][ci][ky][kx]
+ *       layer 3: tile[q][co < 3][tap*8 + ci]        = W3[co][ci][ky_tap][kx_tap] for the q-th tap PAIR
+ *                (q < 10: (2(q/5), q%5) + one row down; q >= 10: (4, 2(q-10)) + one pixel right, the
+ *                 phantom sixth column is zero)
+ *     then fp32 s1[16] b1[16] s2[8] b2[8] b3[4] (+ padding to 256 B): y = acc * s + b per layer.
+ *   max_ctas: 0 = two persistent CTAs per SM, otherwise an upper bound on the grid. */
+int forge_decoder_tc_wpack_bytes(void);
+int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, float* rgb_nchw, int N, int S_h, int S_w,
+                         int max_ctas, void* stream);
+
+/* Test hook: ONE tcgen05.mma (M=128, N=16, K=16, bf16 x bf16 -> fp32, both operands K-major without
+ * swizzle) over a caller-built shared-memory image; pins the descriptor semantics the decoder relies on:
+ *   A[m][k] at a_off + (k/8) a_lbo + (m/8) a_sbo + (m%8) 16 + (k%8) 2,   B[n][k] likewise,   D = A B^T. */
+int forge_umma_probe(const void* image, int image_bytes, unsigned a_off, unsigned a_lbo, unsigned a_sbo,
+                     unsigned b_off, unsigned b_lbo, unsigned b_sbo, float* out_128x16, void* stream);
 
 /* ---- K2: affine feature-volume resample ---------------------------------------------------
  * Replaces models/rotate.py:127-141: materialised homogeneous grid, matmul with T^T, divide by

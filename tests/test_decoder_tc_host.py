@@ -1,0 +1,133 @@
+"""CPU check of the tensor-core decoder's HOST side: the bf16 B-tile weight pack and the flattened implicit-GEMM
+index plan of decoder_tc.cu are replayed in torch (descriptor reads emulated with the canonical no-swizzle K-major
+layout) and compared with the straightforward convolutions.  No GPU, no library compute calls."""
+import struct
+
+import torch
+import torch.nn.functional as F
+
+from forge_b200 import ops, synthetic as syn
+from forge_b200.models.volume_render import VolRender
+
+TOX, TOY, IN_W, L1_W = 32, 16, 22, 40
+IN_PLANE, L1_PLANE, L2_PLANE = 432, 1064, 896
+W1_OFF, W2_OFF, W3_OFF, PRM_OFF, BTILE = 0, 36 * 512, 61 * 512, 74 * 512, 512
+
+
+def _operand(mem_bf16, off, lbo, sbo, rows):
+    r = torch.arange(rows).view(-1, 1)
+    k = torch.arange(16).view(1, -1)
+    idx = (off + (k // 8) * lbo + (r // 8) * sbo + (r % 8) * 16 + (k % 8) * 2) // 2
+    return mem_bf16[idx].float()
+
+
+def _mma(act, a_off, a_lbo, wmem, b_off):
+    return _operand(act, a_off, a_lbo, 128, 128) @ _operand(wmem, b_off, 256, 128, 16).t()
+
+
+def _lrelu(v):
+    return torch.where(v > 0, v, 0.01 * v)
+
+
+def replay_tile(x_nhwc, pack_u8, n, Y0, X0, out):
+    Sh, Sw = x_nhwc.shape[1:3]
+    OH, OW = 2 * Sh, 2 * Sw
+    wmem = pack_u8[:PRM_OFF].view(torch.bfloat16)
+    prm = pack_u8[PRM_OFF:].view(torch.float32)
+    s1, b1, s2, b2, b3 = prm[0:16], prm[16:32], prm[32:40], prm[40:48], prm[48:51]
+    sIn = torch.zeros(2 * IN_PLANE * 8, dtype=torch.bfloat16)
+    sL1 = torch.zeros(2 * L1_PLANE * 8, dtype=torch.bfloat16)
+    sL2 = torch.zeros(L2_PLANE * 8, dtype=torch.bfloat16)
+    for px in range(14 * IN_W):
+        r, c = divmod(px, IN_W)
+        iy, ix = Y0 // 2 - 3 + r, X0 // 2 - 3 + c
+        if 0 <= iy < Sh and 0 <= ix < Sw:
+            for half in (0, 1):
+                sIn[(half * IN_PLANE + px) * 8:(half * IN_PLANE + px) * 8 + 8] = x_nhwc[n, iy, ix, half * 8:half * 8 + 8].to(torch.bfloat16)
+    for cls in range(4):
+        py, pxc = cls >> 1, cls & 1
+        for j in range(3):
+            acc = torch.zeros(128, 16)
+            for t in range(9):
+                a, b = divmod(t, 3)
+                acc += _mma(sIn, (j * 128 + a * IN_W + b) * 16, IN_PLANE * 16, wmem, W1_OFF + (cls * 9 + t) * BTILE)
+            for row in range(128):
+                yr, xr = divmod(j * 128 + row, IN_W)
+                if yr < TOY // 2 + 4 and xr < TOX // 2 + 4:
+                    lr, lc = 2 * yr + py, 2 * xr + pxc
+                    oy, ox = Y0 - 4 + lr, X0 - 4 + lc
+                    v = _lrelu(acc[row] * s1 + b1) if (0 <= oy < OH and 0 <= ox < OW) else torch.zeros(16)
+                    idx = lr * L1_W + lc
+                    sL1[idx * 8:idx * 8 + 8] = v[:8].to(torch.bfloat16)
+                    sL1[(L1_PLANE + idx) * 8:(L1_PLANE + idx) * 8 + 8] = v[8:].to(torch.bfloat16)
+    for j in range(7):
+        acc = torch.zeros(128, 16)
+        for t in range(25):
+            ky, kx = divmod(t, 5)
+            acc += _mma(sL1, (j * 128 + ky * L1_W + kx) * 16, L1_PLANE * 16, wmem, W2_OFF + t * BTILE)
+        for row in range(128):
+            m = j * 128 + row
+            yr, xr = divmod(m, L1_W)
+            oy, ox = Y0 - 2 + yr, X0 - 2 + xr
+            v = _lrelu(acc[row, :8] * s2 + b2) if (0 <= oy < OH and 0 <= ox < OW) else torch.zeros(8)
+            sL2[m * 8:m * 8 + 8] = v.to(torch.bfloat16)
+    for j in range(5):
+        acc = torch.zeros(128, 16)
+        for q in range(13):
+            shift = (2 * (q // 5)) * L1_W + (q % 5) if q < 10 else 4 * L1_W + 2 * (q - 10)
+            lbo = L1_W * 16 if q < 10 else 16
+            acc += _mma(sL2, (j * 128 + shift) * 16, lbo, wmem, W3_OFF + q * BTILE)
+        for row in range(128):
+            yr, xr = divmod(j * 128 + row, L1_W)
+            oy, ox = Y0 + yr, X0 + xr
+            if yr < TOY and xr < TOX and oy < OH and ox < OW:
+                out[n, :, oy, ox] = torch.relu(acc[row, :3] + b3)
+
+
+def test_weight_pack_and_index_plan_replay():
+    torch.manual_seed(0)
+    m = VolRender(syn.make_config(img_size=80, n_pts_per_ray=8))
+    for mod in m.conv_rgb:
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.3)
+            mod.running_var.uniform_(0.5, 2.0)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.2)
+    m.eval()
+    import forge_b200._lib as L
+    pack = ops.pack_decoder_tc_weights(m.conv_rgb)
+    assert pack.dtype == torch.uint8 and pack.numel() == L.load().forge_decoder_tc_wpack_bytes() == PRM_OFF + 256
+    Sh, Sw = 12, 20                                     # 24 x 40 output: 2 x 2 tiles, ragged in both directions
+    x = torch.randn(1, Sh, Sw, 16)
+    out = torch.full((1, 3, 2 * Sh, 2 * Sw), float('nan'))
+    for Y0 in range(0, 2 * Sh, TOY):
+        for X0 in range(0, 2 * Sw, TOX):
+            replay_tile(x, pack, 0, Y0, X0, out)
+    assert torch.isfinite(out).all()
+
+    def r16(t):
+        return t.to(torch.bfloat16).float()
+    ct, bn1, _, c2, bn2, _, c3 = m.conv_rgb
+    with torch.no_grad():
+        s1 = bn1.weight / torch.sqrt(bn1.running_var + bn1.eps)
+        s2 = bn2.weight / torch.sqrt(bn2.running_var + bn2.eps)
+        b1 = (ct.bias - bn1.running_mean) * s1 + bn1.bias
+        b2 = (c2.bias - bn2.running_mean) * s2 + bn2.bias
+        y = F.conv_transpose2d(r16(x.permute(0, 3, 1, 2)), r16(ct.weight), None, stride=2, padding=2)
+        y = r16(F.leaky_relu(y * s1.view(1, -1, 1, 1) + b1.view(1, -1, 1, 1), 0.01))
+        y = F.conv2d(y, r16(c2.weight), None, padding=2)
+        y = r16(F.leaky_relu(y * s2.view(1, -1, 1, 1) + b2.view(1, -1, 1, 1), 0.01))
+        ref = F.relu(F.conv2d(y, r16(c3.weight), c3.bias, padding=2))
+        ref32 = F.relu(m.conv_rgb(x.permute(0, 3, 1, 2)))
+    scale = max(1.0, ref.abs().max().item())
+    assert (out - ref).abs().max().item() <= 4e-3 * scale
+    assert (out - ref32).abs().max().item() <= 6e-2 * scale
+
+
+def test_tap_pairs_cover_the_5x5_filter_once():
+    seen = []
+    for ta, tb in ops.decoder_tc_taps3():
+        seen.append(ta)
+        if tb is not None:
+            seen.append(tb)
+    assert sorted(seen) == [(ky, kx) for ky in range(5) for kx in range(5)]

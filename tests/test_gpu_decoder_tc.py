@@ -1,0 +1,126 @@
+"""GPU parity tests of the tensor-core (bf16, tcgen05) decoder and of the UMMA descriptor contract it relies on.
+
+Tolerances (bf16 path, BASELINE.json configs[2]):
+  * vs an fp32 emulation that rounds to bf16 at exactly the kernel's rounding points (input, weights, the two
+    hidden activations): max-abs <= 4e-3 * max(1, |ref|max) -- only accumulation order and rare rounding-boundary
+    flips of a hidden activation differ;
+  * vs the fp32 module (what the reference computes): max-abs <= 6e-2 * max(1, |ref|max), mean-abs <= 6e-3.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from forge_b200 import ops, synthetic as syn            # noqa: E402
+from forge_b200.models.volume_render import VolRender  # noqa: E402
+
+DEV = 'cuda'
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _probe_expected(img_bf16, off, lbo, sbo, rows):
+    """M[r][k] = image[(off + (k // 8) * lbo + (r // 8) * sbo + (r % 8) * 16 + (k % 8) * 2) / 2] (the no-swizzle K-major
+    canonical layout of cute::UMMA::make_umma_desc<Major::K>, LayoutType::INTERLEAVE)."""
+    r = torch.arange(rows).view(-1, 1)
+    k = torch.arange(16).view(1, -1)
+    idx = (off + (k // 8) * lbo + (r // 8) * sbo + (r % 8) * 16 + (k % 8) * 2) // 2
+    return img_bf16[idx].float()
+
+
+PROBE_CASES = [
+    # (a_off, a_lbo, a_sbo)                    what the decoder needs
+    (0, 2048, 128),                           # aligned start, planes 2 KiB apart
+    (16, 2048, 128),                          # start shifted by one pixel (16 B): a filter tap
+    (16 * 45, 6912, 128),                     # layer-1 geometry: tap (2, 1) on pitch 22, plane stride 432 px
+    (16 * 164, 17024, 128),                   # layer-2 geometry: tap (4, 4) on pitch 40, plane stride 1064 px
+    (16 * 83, 640, 128),                      # layer-3: second K half = the pixel one row down (LBO = 40 px)
+    (16 * 164, 16, 128),                      # layer-3: second K half = the next pixel (LBO = 16 B)
+]
+
+
+@pytest.mark.parametrize("a_off,a_lbo,a_sbo", PROBE_CASES)
+def test_umma_descriptor_contract(a_off, a_lbo, a_sbo):
+    torch.manual_seed(a_off + a_lbo)
+    nbytes = 48 * 1024
+    img = (torch.randint(-8, 9, (nbytes // 2,)).float() / 4).to(torch.bfloat16)       # exactly representable, exact sums
+    b_off = 40 * 1024
+    out = ops.umma_probe(img.view(torch.uint8).to(DEV), a_off, a_lbo, a_sbo, b_off, 256, 128).cpu()
+    A = _probe_expected(img, a_off, a_lbo, a_sbo, 128)
+    B = _probe_expected(img, b_off, 256, 128, 16)
+    assert torch.equal(out, A @ B.t())
+
+
+def _randomise_bn(m):
+    for mod in m.conv_rgb:
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.3)
+            mod.running_var.uniform_(0.5, 2.0)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.2)
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def emulate_bf16_decoder(conv_rgb, x_nhwc):
+    """fp64 evaluation with bf16 rounding at the kernel's rounding points."""
+    ct, bn1, _, c2, bn2, _, c3 = conv_rgb
+    d = torch.float64
+    s1 = (bn1.weight / torch.sqrt(bn1.running_var + bn1.eps)).to(d)
+    s2 = (bn2.weight / torch.sqrt(bn2.running_var + bn2.eps)).to(d)
+    b1 = (ct.bias.to(d) - bn1.running_mean.to(d)) * s1 + bn1.bias.to(d)
+    b2 = (c2.bias.to(d) - bn2.running_mean.to(d)) * s2 + bn2.bias.to(d)
+    x = _bf16_round(x_nhwc.permute(0, 3, 1, 2).float()).to(d)
+    y = F.conv_transpose2d(x, _bf16_round(ct.weight.float()).to(d), None, stride=2, padding=2)
+    y = F.leaky_relu(y * s1.view(1, -1, 1, 1) + b1.view(1, -1, 1, 1), 0.01)
+    y = _bf16_round(y.float()).to(d)
+    y = F.conv2d(y, _bf16_round(c2.weight.float()).to(d), None, padding=2)
+    y = F.leaky_relu(y * s2.view(1, -1, 1, 1) + b2.view(1, -1, 1, 1), 0.01)
+    y = _bf16_round(y.float()).to(d)
+    y = F.conv2d(y, _bf16_round(c3.weight.float()).to(d), c3.bias.to(d), padding=2)
+    return F.relu(y)
+
+
+@pytest.mark.parametrize("N,Sh,Sw", [(2, 16, 16), (1, 21, 21), (1, 8, 40), (3, 64, 64), (1, 5, 3), (20, 128, 128)])
+def test_decoder_tc_matches_bf16_emulation_and_fp32_module(N, Sh, Sw):
+    torch.manual_seed(N * 1000 + Sh * 10 + Sw)
+    m = VolRender(syn.make_config(img_size=2 * Sh, n_pts_per_ray=8)).to(DEV)
+    _randomise_bn(m)
+    m.eval()
+    x = torch.randn(N, Sh, Sw, 16, device=DEV)
+    with torch.no_grad():
+        out = ops.decoder_tc(x, ops.pack_decoder_tc_weights(m.conv_rgb), m.conv_rgb)
+        ref32 = F.relu(m.conv_rgb(x.permute(0, 3, 1, 2)))
+        emu = emulate_bf16_decoder(m.conv_rgb, x).float()
+    assert out.shape == ref32.shape == (N, 3, 2 * Sh, 2 * Sw)
+    assert torch.isfinite(out).all()
+    scale = max(1.0, ref32.abs().max().item())
+    e_emu = (out - emu).abs().max().item()
+    e_32 = (out - ref32).abs()
+    print("decoder_tc N=%d %dx%d: vs bf16 emulation %.2e, vs fp32 module max %.2e mean %.2e (scale %.2f)"
+          % (N, Sh, Sw, e_emu, e_32.max().item(), e_32.mean().item(), scale))
+    assert e_emu <= 4e-3 * scale
+    assert e_32.max().item() <= 6e-2 * scale and e_32.mean().item() <= 6e-3 * scale
+
+
+def test_decoder_tc_small_grid_and_module_switch():
+    """Persistent loop with fewer CTAs than tiles gives identical bits; VolRender.decode picks the kernel when
+    decoder_dtype is bf16 in eval mode; gradients flow (backward = the module's convs)."""
+    torch.manual_seed(5)
+    m = VolRender(syn.make_config(img_size=96, n_pts_per_ray=8)).to(DEV)
+    _randomise_bn(m)
+    m.eval()
+    x = torch.randn(3, 48, 48, 16, device=DEV)
+    pack = ops.pack_decoder_tc_weights(m.conv_rgb)
+    with torch.no_grad():
+        full = ops.decoder_tc(x, pack, m.conv_rgb)
+        few = ops.decoder_tc(x, pack, m.conv_rgb, max_ctas=5)
+        m.decoder_dtype = torch.bfloat16
+        via_module = m.decode(x)
+    assert torch.equal(full, few) and torch.equal(full, via_module)
+    xg = x.clone().requires_grad_(True)
+    m.decode(xg).sum().backward()
+    assert torch.isfinite(xg.grad).all() and xg.grad.abs().sum() > 0

@@ -114,6 +114,11 @@ def main():
             ms, best = timeit(lambda: m.decode(x), args.reps, flush)
             report("decoder FUSED fp32 kernel (forge_decoder_fwd)", ms, best, None,
                    fp32_TFLOPs=round(N * (2 * S) ** 2 * 6104 * 2 / ms / 1e9, 2))
+            m.decoder_dtype = torch.bfloat16
+            ms, best = timeit(lambda: m.decode(x), args.reps, flush)
+            report("decoder TENSOR-CORE bf16 kernel (forge_decoder_tc_fwd, tcgen05)", ms, best, (x.numel() + N * 3 * img * img) * 4,
+                   bf16_TFLOPs_useful=round(N * (2 * S) ** 2 * 6104 * 2 / ms / 1e9, 2))
+            m.decoder_dtype = None
             m.fused_decoder = False
             for name, setup in (("fp32 (TF32 allowed, torch default)", lambda: None),
                                 ("fp32 strict (allow_tf32=False)", lambda: setattr(torch.backends.cudnn, 'allow_tf32', False)),
