@@ -2,26 +2,37 @@
 // operands / fp32 accumulation on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM)
 // -- the "bf16 decoder" of BASELINE.json configs[2].  Inference only (BatchNorm in eval mode).
 //
-// Every layer is an implicit GEMM with NO im2col: activations sit in shared memory as
-//   plane[c / 8][pixel][c % 8]   (bf16: one pixel of one plane = 16 bytes, pixels row-major, pitch P)
-// which is exactly the un-swizzled K-major "core matrix" layout of a UMMA operand: 8 consecutive
-// pixels x 8 channels = one 8x16-byte core matrix, SBO (next 8 rows) = 128 B, LBO (next 8 values
-// of K) = the plane stride.  Row m of the A operand is the pixel with flattened index m, so a
-// filter tap (ky, kx) is the SAME descriptor with its start address advanced by (ky*P + kx)*16 B:
-// one tcgen05.mma (M=128 pixels, N=16 output channels, K=16) per tap and 128 flattened pixels.
-// Flattened pixels that fall in the halo columns compute garbage that is never read back.
+// Every layer is an implicit GEMM with NO im2col.  Activations sit in shared memory as planes of
+// 16-byte records (8 bf16 channels of one pixel), records of consecutive A-rows 16 bytes apart --
+// exactly the un-swizzled K-major "core matrix" layout of a UMMA operand (8 rows x 16 B contiguous,
+// SBO = 128 B to the next 8 rows, LBO = distance to the next 8 values of K).  Row m of the A
+// operand is the record with flattened index m, so a filter tap is the SAME descriptor with its
+// start address advanced: one tcgen05.mma (M = 128 rows, K = 16) per tap and 128 flattened rows.
+// Rows that fall into halo / wrap-around positions compute garbage that is never read back (an
+// MMA row only depends on its own A row, so garbage stays in its row).
+//
+// The operand reads of the MMAs (4 KB of A + B per instruction through the shared-memory data
+// pipe) are what bounds this kernel (ncu: l1tex__data_pipe_tc_wavefronts), so the plan maximises N:
 //
 //   layer 1  ConvTranspose2d(16->16, k6, s2, p2) = four 3x3 convolutions (one per output parity
-//            class), K = 16 input channels per tap: 4 classes x 3 M-tiles x 9 taps
-//   layer 2  Conv2d(16->8, k5): 7 M-tiles x 25 taps (N padded 8 -> 16)
-//   layer 3  Conv2d(8->3, k5): the input has ONE 8-channel plane, so K = 16 covers TWO taps whose
-//            distance is put into LBO (640 B = one row down, or 16 B = one pixel right):
-//            5 M-tiles x 13 MMAs (N padded 3 -> 16)
+//            class) over the SAME 9 input shifts: N = 64 = (class, co); rows = input pixels
+//            (pitch 22): 3 M-tiles x 9 MMAs.
+//   layer 2  Conv2d(16->8, k5).  Layer-1 pixels are stored in 8 PHASE planes by column
+//            (lc % 8, record index = row * 5 + lc / 8), so one A row = a group of 8 horizontally
+//            adjacent output pixels: N = 64 = (delta, co), and source column j = delta + kx
+//            (0..11) is plane j % 8 shifted by j / 8 records: 1 M-tile x 5 ky x 12 columns = 60 MMAs.
+//            The B operand of column j holds W2[ky][kx = j - delta] in its delta-th 8-row block; all 12
+//            are windows (start block 12 - j, SBO = 128 B) into ONE strip [8 x zero, W(4), ..., W(0)].
+//   layer 3  Conv2d(8->3, k5), same phase-plane scheme on the layer-2 planes (one 8-channel
+//            record per pixel); K = 16 covers the rows ky and ky + 1 (A: LBO = 5 records = one row
+//            down; B: LBO = one strip): 1 M-tile x 3 ky-pairs x 12 columns = 36 MMAs, N = 64 =
+//            (delta, co padded to 8).
 //
-// Epilogues (tcgen05.ld, one accumulator row per thread) apply scale/shift (folded BN + bias),
-// LeakyReLU, the zero padding of the next convolution, and write bf16 planes for the next layer;
-// the last one applies ReLU and stores fp32 NCHW.  Weights (37 KB of prebuilt B tiles) arrive by
-// one bulk async copy (TMA engine).  Persistent CTAs, 2 per SM (100 KB smem, 256 TMEM columns).
+// Epilogues (tcgen05.ld, one accumulator row per thread, the two warp groups split the columns)
+// apply scale/shift (folded BN + bias), LeakyReLU, the zero padding of the next convolution, and
+// write bf16 phase planes for the next layer; the last one applies ReLU and stores fp32 NCHW as
+// float4.  Weights (46 KB of prebuilt B tiles / strips) arrive by one bulk async copy (TMA engine).
+// Persistent CTAs, 2 per SM (104 KB smem, 256 TMEM columns each).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -31,28 +42,34 @@ namespace dtc {
 
 constexpr int kThreads = 256;
 constexpr int TOX = 32, TOY = 16;                 // output tile
-constexpr int IN_W = TOX / 2 + 6, IN_H = TOY / 2 + 6;     // 22 x 14 input pixels
-constexpr int L1_W = TOX + 8, L1_H = TOY + 8;             // 40 x 24 layer-1 pixels; 40 is also the layer-2 pitch
-constexpr int M1_TILES = 3, M2_TILES = 7, M3_TILES = 5;   // 128-row tiles of flattened pixels per layer
-constexpr int IN_PLANE = 432;                     // >= 3*128 + 2*22 + 2
-constexpr int L1_PLANE = 1064;                    // >= 7*128 + 4*40 + 4
-constexpr int L2_PLANE = 896;                     // = 7*128 >= 5*128 + 4*40 + 5
+constexpr int IN_W = TOX / 2 + 6, IN_H = TOY / 2 + 6;     // 22 x 14 input pixels (pitch 22)
+constexpr int L1_W = TOX + 8;                     // 40 x 24 layer-1 pixels = 5 groups of 8 per row
+constexpr int GP = L1_W / 8;                      // record pitch of the phase planes (groups per row)
+constexpr int M1_TILES = 3;                       // 128-row tiles of flattened input pixels in layer 1
+constexpr int IN_PLANE = 432;                     // records per input channel-chunk plane >= 3*128 + 2*22 + 2
+constexpr int L1_PLANE = 152;                     // records per layer-1 plane >= 128 + 4*5 + 1
+constexpr int L2_PLANE = 160;                     // records per layer-2 plane >= 128 + 5*5 + 1
+static_assert(L1_W % 8 == 0 && GP == 5, "phase planes assume 8-pixel groups");
 static_assert(IN_PLANE >= M1_TILES * 128 + 2 * IN_W + 2, "input plane too small for the flattened over-read");
-static_assert(L1_PLANE >= M2_TILES * 128 + 4 * L1_W + 4, "layer-1 plane too small");
-static_assert(L2_PLANE >= M3_TILES * 128 + 4 * L1_W + 5 && L2_PLANE >= M2_TILES * 128, "layer-2 plane too small");
-static_assert((TOY / 2 + 4) * IN_W <= M1_TILES * 128 && (TOY + 4) * L1_W <= M2_TILES * 128 && TOY * L1_W <= M3_TILES * 128,
-              "M tiles do not cover the layer");
+static_assert(L1_PLANE >= 128 + 4 * GP + 1 && L2_PLANE >= 128 + 5 * GP + 1, "phase plane too small for the over-read");
+static_assert((TOY / 2 + 4) * IN_W <= M1_TILES * 128 && (TOY + 4) * GP <= 128 && TOY * GP <= 128, "M tiles do not cover the layer");
 
-constexpr int BTILE = 512;                        // one B tile: [k/8][n = 16][k%8] bf16
-constexpr int W1_OFF = 0, W2_OFF = W1_OFF + 36 * BTILE, W3_OFF = W2_OFF + 25 * BTILE, PRM_OFF = W3_OFF + 13 * BTILE;
-constexpr int WPACK_BYTES = PRM_OFF + 256;        // 38144
-constexpr int SM_W = 0, SM_IN = SM_W + WPACK_BYTES, SM_L1 = SM_IN + 2 * IN_PLANE * 16, SM_L2 = SM_L1 + 2 * L1_PLANE * 16,
-              SM_BAR = SM_L2 + L2_PLANE * 16, SM_TOTAL = SM_BAR + 32;
-constexpr int TMEM_COLS = 256;                    // 12 accumulators x 16 columns in layer 1
+constexpr int BLK = 128;                          // one 8 x 8 bf16 core matrix
+constexpr int STRIP = 13 * BLK;                   // [8 x zero][W(kx=4) .. W(kx=0)]
+constexpr int W1_TILE = 2048;                     // [k/8][n = 64][k%8]
+constexpr int W1_OFF = 0, W2_OFF = W1_OFF + 9 * W1_TILE, W3_OFF = W2_OFF + 10 * STRIP + 8 * BLK,
+              PRM_OFF = W3_OFF + 6 * STRIP + 8 * BLK;
+constexpr int WPACK_BYTES = PRM_OFF + 256;        // 47360
+// the input planes alias the layer-2 planes: the former are dead once layer 1's MMAs have completed
+constexpr int SM_W = 0, SM_L1 = SM_W + WPACK_BYTES, SM_L2 = SM_L1 + 16 * L1_PLANE * 16, SM_IN = SM_L2,
+              SM_BAR = SM_L2 + 8 * L2_PLANE * 16, SM_TOTAL = SM_BAR + 32;
+static_assert(2 * IN_PLANE * 16 <= 8 * L2_PLANE * 16, "input planes must fit in the layer-2 region they alias");
+constexpr int TMEM_COLS = 256;                    // layer 1: 3 x 64 columns, layer 2: 64 (192..255), layer 3: 64 (0..63)
 
 // instruction descriptor (PTX ISA "Instruction descriptor", kind::f16): D = f32, A = B = bf16, both K-major,
-// N = 16, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+// N = 64, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_PROBE = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -88,23 +105,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
-    uint32_t r[4];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -164,15 +182,15 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int e = tid; e < (SM_BAR - SM_IN) / 16; e += kThreads)          // pads must hold finite values
-        reinterpret_cast<uint4*>(sIn)[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = tid; e < (SM_BAR - SM_L1) / 16; e += kThreads)          // over-read pads must hold finite values
+        reinterpret_cast<uint4*>(sL1)[e] = make_uint4(0u, 0u, 0u, 0u);
     mbar_wait(wbar, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);   // this warp's TMEM lane quarter
     const int row = (warp & 3) * 32 + lane, grp = warp >> 2;             // accumulator row of this thread, warp group
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + grp * 32;   // lane quarter, column half
     const uint32_t aIn = smem_u32(sIn), aL1 = smem_u32(sL1), aL2 = smem_u32(sL2), aW = smem_u32(sW);
     uint32_t phase = 0;
 
@@ -181,7 +199,7 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
         const int tyi = t2 / tiles_x, txi = t2 - tyi * tiles_x;
         const int Y0 = tyi * TOY, X0 = txi * TOX;
 
-        // ---- P0: input tile fp32 NHWC -> two bf16 planes (zeros outside the image) ----
+        // ---- P0: input tile fp32 NHWC -> two bf16 channel-chunk planes (zeros outside the image) ----
         {
             const int iy0 = Y0 / 2 - 3, ix0 = X0 / 2 - 3;
             const float4* xin = reinterpret_cast<const float4*>(x) + static_cast<long long>(n) * Sh * Sw * 4;
@@ -203,124 +221,130 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
         tc_fence_before();
         __syncthreads();
 
-        // ---- P1: transposed conv as 4 parity classes x 3 M-tiles x 9 taps ----
-        if (tid == 0) {
-            tc_fence_after();
-#pragma unroll 1
-            for (int cls = 0; cls < 4; ++cls)
-#pragma unroll 1
-                for (int j = 0; j < M1_TILES; ++j) {
-                    const uint32_t d = tmem + (cls * M1_TILES + j) * 16;
+        // ---- P1: transposed conv: 3 M-tiles x 9 input shifts, N = (parity class, co) ----
+        if (warp == 0) {
+            if (elect_one()) {
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < M1_TILES; ++j)
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const int a = t / 3, b = t - a * 3;       // source pixel offset (rows, cols) inside the input tile
-                        umma_bf16(d, make_desc(aIn + (j * 128 + a * IN_W + b) * 16, IN_PLANE * 16, 128),
-                                  make_desc(aW + W1_OFF + (cls * 9 + t) * BTILE, 256, 128), IDESC, t > 0);
+                        umma_bf16(tmem + j * 64, make_desc(aIn + (j * 128 + a * IN_W + b) * 16, IN_PLANE * 16, 128),
+                                  make_desc(aW + W1_OFF + t * W1_TILE, 1024, 128), IDESC, t > 0);
                     }
-                }
-            umma_commit(mbar);
+                umma_commit(mbar);
+            }
+            __syncwarp();
         }
         mbar_wait(mbar, phase);
         phase ^= 1;
         tc_fence_after();
 #pragma unroll 1
-        for (int i = 0; i < 6; ++i) {
-            const int ai = 2 * i + grp, cls = ai / M1_TILES, j = ai - cls * M1_TILES, py = cls >> 1, px = cls & 1;
-            float acc[16];
-            tmem_ld16(t_lane + ai * 16, acc);
+        for (int j = 0; j < M1_TILES; ++j) {
+            float acc[32];                                        // classes (py = grp, px = 0) and (py = grp, px = 1)
+            tmem_ld32(t_lane + j * 64, acc);
             const int m = j * 128 + row, yr = m / IN_W, xr = m - yr * IN_W;
             if (yr < TOY / 2 + 4 && xr < TOX / 2 + 4) {
-                const int lr = 2 * yr + py, lc = 2 * xr + px, oy = Y0 - 4 + lr, ox = X0 - 4 + lc;
-                const bool inside = oy >= 0 && oy < OH && ox >= 0 && ox < OW;     // zero padding of layer 2
-                uint32_t q[8];
+                const int lr = 2 * yr + grp, oy = Y0 - 4 + lr;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float v0 = inside ? lrelu(fmaf(acc[2 * c], prm[2 * c], prm[16 + 2 * c])) : 0.f;
-                    const float v1 = inside ? lrelu(fmaf(acc[2 * c + 1], prm[2 * c + 1], prm[16 + 2 * c + 1])) : 0.f;
-                    q[c] = pack_bf16(v0, v1);
+                for (int px = 0; px < 2; ++px) {
+                    const int lc = 2 * xr + px, ox = X0 - 4 + lc;
+                    const bool inside = oy >= 0 && oy < OH && ox >= 0 && ox < OW;     // zero padding of layer 2
+                    uint32_t q[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float v0 = inside ? lrelu(fmaf(acc[px * 16 + 2 * c], prm[2 * c], prm[16 + 2 * c])) : 0.f;
+                        const float v1 = inside ? lrelu(fmaf(acc[px * 16 + 2 * c + 1], prm[2 * c + 1], prm[16 + 2 * c + 1])) : 0.f;
+                        q[c] = pack_bf16(v0, v1);
+                    }
+                    unsigned char* dst = sL1 + (((lc & 7) * 2) * L1_PLANE + lr * GP + (lc >> 3)) * 16;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(q[0], q[1], q[2], q[3]);
+                    *reinterpret_cast<uint4*>(dst + L1_PLANE * 16) = make_uint4(q[4], q[5], q[6], q[7]);
                 }
-                const int idx = lr * L1_W + lc;
-                *reinterpret_cast<uint4*>(sL1 + idx * 16) = make_uint4(q[0], q[1], q[2], q[3]);
-                *reinterpret_cast<uint4*>(sL1 + (L1_PLANE + idx) * 16) = make_uint4(q[4], q[5], q[6], q[7]);
             }
         }
         proxy_fence();
         tc_fence_before();
         __syncthreads();
 
-        // ---- P2: conv 5x5 16 -> 8: 7 M-tiles x 25 taps ----
-        if (tid == 0) {
-            tc_fence_after();
-#pragma unroll 1
-            for (int j = 0; j < M2_TILES; ++j) {
-                const uint32_t d = tmem + j * 16;
+        // ---- P2: conv 5x5 16 -> 8: rows = groups of 8 pixels, 5 ky x 12 source columns ----
+        if (warp == 0) {
+            if (elect_one()) {
+                tc_fence_after();
 #pragma unroll
-                for (int t = 0; t < 25; ++t) {
-                    const int ky = t / 5, kx = t - ky * 5;
-                    umma_bf16(d, make_desc(aL1 + (j * 128 + ky * L1_W + kx) * 16, L1_PLANE * 16, 128),
-                              make_desc(aW + W2_OFF + t * BTILE, 256, 128), IDESC, t > 0);
-                }
+                for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                    for (int j = 0; j < 12; ++j)
+                        umma_bf16(tmem + 192,
+                                  make_desc(aL1 + (((j & 7) * 2) * L1_PLANE + ky * GP + (j >> 3)) * 16, L1_PLANE * 16, 128),
+                                  make_desc(aW + W2_OFF + ky * 2 * STRIP + (12 - j) * BLK, STRIP, 128), IDESC, (ky | j) > 0);
+                umma_commit(mbar);
             }
-            umma_commit(mbar);
+            __syncwarp();
         }
         mbar_wait(mbar, phase);
         phase ^= 1;
         tc_fence_after();
-#pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-            const int j = 2 * i + grp;
-            if (j < M2_TILES) {                                   // warp-uniform
-                float acc[8];
-                tmem_ld8(t_lane + j * 16, acc);
-                const int m = j * 128 + row, yr = m / L1_W, xr = m - yr * L1_W;
-                const int oy = Y0 - 2 + yr, ox = X0 - 2 + xr;
-                const bool inside = oy >= 0 && oy < OH && ox >= 0 && ox < OW;     // zero padding of layer 3
+        {
+            float acc[32];                                        // pixels delta = 4 grp .. 4 grp + 3 of this row's group
+            tmem_ld32(t_lane + 192, acc);
+            const int yr = row / GP, xg = row - yr * GP, oy = Y0 - 2 + yr;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int delta = 4 * grp + d, ox = X0 - 2 + 8 * xg + delta;
+                const bool inside = oy >= 0 && oy < OH && ox >= 0 && ox < OW;         // zero padding of layer 3
                 uint32_t q[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float v0 = inside ? lrelu(fmaf(acc[2 * c], prm[32 + 2 * c], prm[40 + 2 * c])) : 0.f;
-                    const float v1 = inside ? lrelu(fmaf(acc[2 * c + 1], prm[32 + 2 * c + 1], prm[40 + 2 * c + 1])) : 0.f;
+                    const float v0 = inside ? lrelu(fmaf(acc[d * 8 + 2 * c], prm[32 + 2 * c], prm[40 + 2 * c])) : 0.f;
+                    const float v1 = inside ? lrelu(fmaf(acc[d * 8 + 2 * c + 1], prm[32 + 2 * c + 1], prm[40 + 2 * c + 1])) : 0.f;
                     q[c] = pack_bf16(v0, v1);
                 }
-                *reinterpret_cast<uint4*>(sL2 + m * 16) = make_uint4(q[0], q[1], q[2], q[3]);
+                *reinterpret_cast<uint4*>(sL2 + (delta * L2_PLANE + row) * 16) = make_uint4(q[0], q[1], q[2], q[3]);
             }
         }
         proxy_fence();
         tc_fence_before();
         __syncthreads();
 
-        // ---- P3: conv 5x5 8 -> 3: two taps per MMA (LBO = their distance), 5 M-tiles x 13 ----
-        if (tid == 0) {
-            tc_fence_after();
-#pragma unroll 1
-            for (int j = 0; j < M3_TILES; ++j) {
-                const uint32_t d = tmem + j * 16;
+        // ---- P3: conv 5x5 8 -> 3: K = rows (ky, ky + 1), 3 ky pairs x 12 source columns ----
+        if (warp == 0) {
+            if (elect_one()) {
+                tc_fence_after();
 #pragma unroll
-                for (int q = 0; q < 13; ++q) {
-                    // q < 10: taps (ky, kx) and (ky + 1, kx), ky = 2 (q / 5), kx = q % 5; q >= 10: taps (4, kx), (4, kx + 1), kx = 2 (q - 10)
-                    const int shift = q < 10 ? (2 * (q / 5)) * L1_W + (q % 5) : 4 * L1_W + 2 * (q - 10);
-                    const int lbo = q < 10 ? L1_W * 16 : 16;
-                    umma_bf16(d, make_desc(aL2 + (j * 128 + shift) * 16, lbo, 128),
-                              make_desc(aW + W3_OFF + q * BTILE, 256, 128), IDESC, q > 0);
-                }
+                for (int kp = 0; kp < 3; ++kp)
+#pragma unroll
+                    for (int j = 0; j < 12; ++j)
+                        umma_bf16(tmem, make_desc(aL2 + ((j & 7) * L2_PLANE + 2 * kp * GP + (j >> 3)) * 16, GP * 16, 128),
+                                  make_desc(aW + W3_OFF + 2 * kp * STRIP + (12 - j) * BLK, STRIP, 128), IDESC, (kp | j) > 0);
+                umma_commit(mbar);
             }
-            umma_commit(mbar);
+            __syncwarp();
         }
         mbar_wait(mbar, phase);
         phase ^= 1;
         tc_fence_after();
-#pragma unroll 1
-        for (int i = 0; i < 3; ++i) {
-            const int j = 2 * i + grp;
-            if (j < M3_TILES) {
-                float acc[4];
-                tmem_ld4(t_lane + j * 16, acc);
-                const int m = j * 128 + row, yr = m / L1_W, xr = m - yr * L1_W;
-                const int oy = Y0 + yr, ox = X0 + xr;
-                if (yr < TOY && xr < TOX && oy < OH && ox < OW) {
+        {
+            float acc[32];
+            tmem_ld32(t_lane, acc);
+            const int yr = row / GP, xg = row - yr * GP;
+            const int oy = Y0 + yr, ox = X0 + 8 * xg + 4 * grp;
+            if (yr < TOY && xg < TOX / 8 && oy < OH && ox < OW) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        rgb[((static_cast<long long>(n) * 3 + c) * OH + oy) * OW + ox] = fmaxf(acc[c] + prm[48 + c], 0.f);
+                for (int c = 0; c < 3; ++c) {
+                    const float b = prm[48 + c];
+                    float* dst = rgb + ((static_cast<long long>(n) * 3 + c) * OH + oy) * OW + ox;
+                    const float4 v = make_float4(fmaxf(acc[c] + b, 0.f), fmaxf(acc[8 + c] + b, 0.f), fmaxf(acc[16 + c] + b, 0.f),
+                                                 fmaxf(acc[24 + c] + b, 0.f));
+                    if (ox + 3 < OW && (OW & 3) == 0) {
+                        *reinterpret_cast<float4*>(dst) = v;
+                    } else {
+                        dst[0] = v.x;
+                        if (ox + 1 < OW) dst[1] = v.y;
+                        if (ox + 2 < OW) dst[2] = v.z;
+                        if (ox + 3 < OW) dst[3] = v.w;
+                    }
                 }
             }
         }
@@ -358,7 +382,7 @@ umma_probe_kernel(const unsigned char* __restrict__ image, int image_bytes, unsi
     tc_fence_after();
     const uint32_t tmem = slot;
     if (tid == 0) {
-        umma_bf16(tmem, make_desc(smem_u32(smem) + a_off, a_lbo, a_sbo), make_desc(smem_u32(smem) + b_off, b_lbo, b_sbo), IDESC, 0);
+        umma_bf16(tmem, make_desc(smem_u32(smem) + a_off, a_lbo, a_sbo), make_desc(smem_u32(smem) + b_off, b_lbo, b_sbo), IDESC_PROBE, 0);
         umma_commit(&bar);
     }
     mbar_wait(&bar, 0);

@@ -279,49 +279,46 @@ def decoder_fused(x_nhwc, wpack, conv_rgb):
 
 
 # ---- tensor-core (bf16) decoder ------------------------------------------------------------------
-def _btile(mat):
-    """[n <= 16, k <= 16] -> one UMMA B tile [k / 8][n = 16][k % 8] (K-major core matrices, zero padded)."""
-    t = mat.new_zeros(16, 16)
+def _core_blocks(mat):
+    """[n, k] (n, k multiples of 8 after zero padding) -> UMMA K-major tile [k / 8][n][k % 8] (8-row core matrices)."""
+    n, k = -(-mat.shape[0] // 8) * 8, -(-mat.shape[1] // 8) * 8
+    t = mat.new_zeros(n, k)
     t[:mat.shape[0], :mat.shape[1]] = mat
-    return t.view(16, 2, 8).permute(1, 0, 2).contiguous()
+    return t.view(n, k // 8, 8).permute(1, 0, 2).contiguous()
 
 
-def decoder_tc_taps3():
-    """The 13 tap pairs ((kyA, kxA), (kyB, kxB) | None) of layer 3, in the order decoder_tc.cu issues them."""
-    pairs = []
-    for q in range(13):
-        if q < 10:
-            ky, kx = 2 * (q // 5), q % 5
-            pairs.append(((ky, kx), (ky + 1, kx)))
-        else:
-            kx = 2 * (q - 10)
-            pairs.append(((4, kx), (4, kx + 1) if kx + 1 < 5 else None))
-    return pairs
+def _strip(w_kx):
+    """One weight strip of decoder_tc.cu: 13 core matrices [8 x zero, W(kx=4), W(3), W(2), W(1), W(0)], each [8 n][8 k].
+    The B operand of source column j is the window of 8 blocks starting at block 12 - j."""
+    s = w_kx[0].new_zeros(13, 8, 8)
+    for kx in range(5):
+        blk = w_kx[kx]
+        s[12 - kx, :blk.shape[0], :blk.shape[1]] = blk
+    return s
 
 
 def pack_decoder_tc_weights(conv_rgb):
-    """Weight pack for forge_decoder_tc_fwd from the reference-shaped ``conv_rgb`` Sequential in eval mode:
-    bf16 B tiles (36 + 25 + 13 tiles of 512 B) followed by the fp32 epilogue constants
-    s1[16] b1[16] s2[8] b2[8] b3[4] (BN scale/shift with the conv bias folded in); layout in forge_b200.h."""
+    """Weight pack for forge_decoder_tc_fwd from the reference-shaped ``conv_rgb`` Sequential in eval mode: bf16
+    B operands (9 layer-1 tiles, 10 + 6 strips) followed by the fp32 epilogue constants s1[16] b1[16] s2[8] b2[8]
+    b3[4] (BN scale/shift with the conv bias folded in); layout documented in forge_b200.h."""
     ct, bn1, _, c2, bn2, _, c3 = conv_rgb
     with torch.no_grad():
         wt, w2, w3 = ct.weight.float(), c2.weight.float(), c3.weight.float()
-        tiles = []
-        for py in (0, 1):
-            for px in (0, 1):
-                for a in range(3):
-                    for b in range(3):
-                        tiles.append(_btile(wt[:, :, py + 4 - 2 * a, px + 4 - 2 * b].t()))        # [co, ci]
-        for ky in range(5):
-            for kx in range(5):
-                tiles.append(_btile(w2[:, :, ky, kx]))                                          # [co 8, ci 16]
-        for ta, tb in decoder_tc_taps3():
-            m = wt.new_zeros(3, 16)
-            m[:, :8] = w3[:, :, ta[0], ta[1]]
-            if tb is not None:
-                m[:, 8:] = w3[:, :, tb[0], tb[1]]
-            tiles.append(_btile(m))
-        wb = torch.stack(tiles).to(torch.bfloat16).contiguous().view(torch.uint8).reshape(-1)
+        parts = []
+        for a in range(3):                       # layer 1: one [64 = (py, px, co)] x [16 ci] tile per input shift (a, b)
+            for b in range(3):
+                rows = [wt[:, :, py + 4 - 2 * a, px + 4 - 2 * b].t() for py in (0, 1) for px in (0, 1)]   # each [co, ci]
+                parts.append(_core_blocks(torch.cat(rows, dim=0)).reshape(-1))
+        zeros8 = wt.new_zeros(8 * 64)
+        for ky in range(5):                      # layer 2: strips (ky, ci chunk)
+            for c in range(2):
+                parts.append(_strip([w2[:, 8 * c:8 * c + 8, ky, kx] for kx in range(5)]).reshape(-1))
+        parts.append(zeros8)
+        for ky in range(5):                      # layer 3: strips ky, a phantom all-zero strip ky = 5
+            parts.append(_strip([w3[:, :, ky, kx] for kx in range(5)]).reshape(-1))
+        parts.append(wt.new_zeros(13 * 64))
+        parts.append(zeros8)
+        wb = torch.cat(parts).to(torch.bfloat16).contiguous().view(torch.uint8)
         s1 = bn1.weight / torch.sqrt(bn1.running_var + bn1.eps)
         s2 = bn2.weight / torch.sqrt(bn2.running_var + bn2.eps)
         b1 = (ct.bias - bn1.running_mean) * s1 + bn1.bias

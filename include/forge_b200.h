@@ -100,14 +100,16 @@ int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float* rgb_nchw, 
  * BN -- computed as implicit GEMMs on the 5th-generation tensor cores: the "bf16 decoder" of
  * BASELINE.json configs[2].  Inputs/outputs stay fp32 (x is rounded to bf16 on load, the two hidden
  * activations are rounded to bf16 after BN + LeakyReLU); deviation from the fp32 module ~1e-2.
- *   wpack (forge_decoder_tc_wpack_bytes() bytes, 16-byte aligned) =
- *     36 + 25 + 13 B tiles of 512 B, each [k/8][n = 16][k%8] bf16 (un-swizzled K-major core matrices):
- *       layer 1: tile[(py*2+px)*9 + a*3+b][co][ci] = Wt[ci][co][py+4-2a][px+4-2b]
- *       layer 2: tile[ky*5+kx][co < 8][ci]          = W2[co][ci][ky][kx]
- *       layer 3: tile[q][co < 3][tap*8 + ci]        = W3[co][ci][ky_tap][kx_tap] for the q-th tap PAIR
- *                (q < 10: (2(q/5), q%5) + one row down; q >= 10: (4, 2(q-10)) + one pixel right, the
- *                 phantom sixth column is zero)
- *     then fp32 s1[16] b1[16] s2[8] b2[8] b3[4] (+ padding to 256 B): y = acc * s + b per layer.
+ *   wpack (forge_decoder_tc_wpack_bytes() bytes, 16-byte aligned) = bf16 UMMA B operands built from 8 x 8
+ *   core matrices blk[n % 8][k % 8] (128 B, un-swizzled K-major), then the fp32 epilogue constants:
+ *     layer 1: 9 tiles (input shift a*3+b) of [k/8 = 2][n = 64][k%8]: n = (py*2+px)*16 + co, k = ci,
+ *              value Wt[ci][co][py+4-2a][px+4-2b]
+ *     layer 2: 10 strips (ky*2 + ci/8) of 13 blocks [8 x zero, W(kx=4), .., W(kx=0)], W(kx)[co][ci%8] =
+ *              W2[co][ci][ky][kx]; then 8 zero blocks.  The B operand of source column j (0..11) is the 8-block
+ *              window starting at block 12-j: block delta holds W(kx = j - delta) or zero.
+ *     layer 3: 5 strips (ky) of the same shape with W(kx)[co < 3][ci] = W3[co][ci][ky][kx], one all-zero strip
+ *              (the phantom row ky = 5), then 8 zero blocks.
+ *     fp32 s1[16] b1[16] s2[8] b2[8] b3[4] (+ padding to 256 B): y = acc * s + b per layer.
  *   max_ctas: 0 = two persistent CTAs per SM, otherwise an upper bound on the grid. */
 int forge_decoder_tc_wpack_bytes(void);
 int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, float* rgb_nchw, int N, int S_h, int S_w,

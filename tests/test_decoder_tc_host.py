@@ -9,20 +9,25 @@ import torch.nn.functional as F
 from forge_b200 import ops, synthetic as syn
 from forge_b200.models.volume_render import VolRender
 
-TOX, TOY, IN_W, L1_W = 32, 16, 22, 40
-IN_PLANE, L1_PLANE, L2_PLANE = 432, 1064, 896
-W1_OFF, W2_OFF, W3_OFF, PRM_OFF, BTILE = 0, 36 * 512, 61 * 512, 74 * 512, 512
+TOX, TOY, IN_W, GP = 32, 16, 22, 5
+IN_PLANE, L1_PLANE, L2_PLANE = 432, 152, 160
+BLK, STRIP, W1_TILE = 128, 13 * 128, 2048
+W1_OFF = 0
+W2_OFF = W1_OFF + 9 * W1_TILE
+W3_OFF = W2_OFF + 10 * STRIP + 8 * BLK
+PRM_OFF = W3_OFF + 6 * STRIP + 8 * BLK
 
 
 def _operand(mem_bf16, off, lbo, sbo, rows):
+    """Rows of a K-major un-swizzled UMMA operand (K = 16) read through a descriptor (start, LBO, SBO) in bytes."""
     r = torch.arange(rows).view(-1, 1)
     k = torch.arange(16).view(1, -1)
     idx = (off + (k // 8) * lbo + (r // 8) * sbo + (r % 8) * 16 + (k % 8) * 2) // 2
     return mem_bf16[idx].float()
 
 
-def _mma(act, a_off, a_lbo, wmem, b_off):
-    return _operand(act, a_off, a_lbo, 128, 128) @ _operand(wmem, b_off, 256, 128, 16).t()
+def _mma(act, a_off, a_lbo, wmem, b_off, b_lbo):
+    return _operand(act, a_off, a_lbo, 128, 128) @ _operand(wmem, b_off, b_lbo, 128, 64).t()
 
 
 def _lrelu(v):
@@ -30,58 +35,64 @@ def _lrelu(v):
 
 
 def replay_tile(x_nhwc, pack_u8, n, Y0, X0, out):
+    """decoder_tc.cu's plan for one 32x16 output tile, MMA by MMA (same descriptors, same epilogue index math)."""
     Sh, Sw = x_nhwc.shape[1:3]
     OH, OW = 2 * Sh, 2 * Sw
     wmem = pack_u8[:PRM_OFF].view(torch.bfloat16)
     prm = pack_u8[PRM_OFF:].view(torch.float32)
     s1, b1, s2, b2, b3 = prm[0:16], prm[16:32], prm[32:40], prm[40:48], prm[48:51]
+    sL1 = torch.zeros(16 * L1_PLANE * 8, dtype=torch.bfloat16)
+    sL2 = torch.zeros(8 * L2_PLANE * 8, dtype=torch.bfloat16)     # the input planes alias this region in the kernel
     sIn = torch.zeros(2 * IN_PLANE * 8, dtype=torch.bfloat16)
-    sL1 = torch.zeros(2 * L1_PLANE * 8, dtype=torch.bfloat16)
-    sL2 = torch.zeros(L2_PLANE * 8, dtype=torch.bfloat16)
     for px in range(14 * IN_W):
         r, c = divmod(px, IN_W)
         iy, ix = Y0 // 2 - 3 + r, X0 // 2 - 3 + c
         if 0 <= iy < Sh and 0 <= ix < Sw:
             for half in (0, 1):
                 sIn[(half * IN_PLANE + px) * 8:(half * IN_PLANE + px) * 8 + 8] = x_nhwc[n, iy, ix, half * 8:half * 8 + 8].to(torch.bfloat16)
-    for cls in range(4):
-        py, pxc = cls >> 1, cls & 1
-        for j in range(3):
-            acc = torch.zeros(128, 16)
-            for t in range(9):
-                a, b = divmod(t, 3)
-                acc += _mma(sIn, (j * 128 + a * IN_W + b) * 16, IN_PLANE * 16, wmem, W1_OFF + (cls * 9 + t) * BTILE)
-            for row in range(128):
-                yr, xr = divmod(j * 128 + row, IN_W)
-                if yr < TOY // 2 + 4 and xr < TOX // 2 + 4:
-                    lr, lc = 2 * yr + py, 2 * xr + pxc
-                    oy, ox = Y0 - 4 + lr, X0 - 4 + lc
-                    v = _lrelu(acc[row] * s1 + b1) if (0 <= oy < OH and 0 <= ox < OW) else torch.zeros(16)
-                    idx = lr * L1_W + lc
-                    sL1[idx * 8:idx * 8 + 8] = v[:8].to(torch.bfloat16)
-                    sL1[(L1_PLANE + idx) * 8:(L1_PLANE + idx) * 8 + 8] = v[8:].to(torch.bfloat16)
-    for j in range(7):
-        acc = torch.zeros(128, 16)
-        for t in range(25):
-            ky, kx = divmod(t, 5)
-            acc += _mma(sL1, (j * 128 + ky * L1_W + kx) * 16, L1_PLANE * 16, wmem, W2_OFF + t * BTILE)
+    # layer 1
+    for j in range(3):
+        acc = torch.zeros(128, 64)
+        for t in range(9):
+            a, b = divmod(t, 3)
+            acc += _mma(sIn, (j * 128 + a * IN_W + b) * 16, IN_PLANE * 16, wmem, W1_OFF + t * W1_TILE, 1024)
         for row in range(128):
-            m = j * 128 + row
-            yr, xr = divmod(m, L1_W)
-            oy, ox = Y0 - 2 + yr, X0 - 2 + xr
-            v = _lrelu(acc[row, :8] * s2 + b2) if (0 <= oy < OH and 0 <= ox < OW) else torch.zeros(8)
-            sL2[m * 8:m * 8 + 8] = v.to(torch.bfloat16)
-    for j in range(5):
-        acc = torch.zeros(128, 16)
-        for q in range(13):
-            shift = (2 * (q // 5)) * L1_W + (q % 5) if q < 10 else 4 * L1_W + 2 * (q - 10)
-            lbo = L1_W * 16 if q < 10 else 16
-            acc += _mma(sL2, (j * 128 + shift) * 16, lbo, wmem, W3_OFF + q * BTILE)
-        for row in range(128):
-            yr, xr = divmod(j * 128 + row, L1_W)
-            oy, ox = Y0 + yr, X0 + xr
-            if yr < TOY and xr < TOX and oy < OH and ox < OW:
-                out[n, :, oy, ox] = torch.relu(acc[row, :3] + b3)
+            yr, xr = divmod(j * 128 + row, IN_W)
+            if yr < TOY // 2 + 4 and xr < TOX // 2 + 4:
+                for py in (0, 1):
+                    for px in (0, 1):
+                        lr, lc = 2 * yr + py, 2 * xr + px
+                        oy, ox = Y0 - 4 + lr, X0 - 4 + lc
+                        col = (py * 2 + px) * 16
+                        v = _lrelu(acc[row, col:col + 16] * s1 + b1) if (0 <= oy < OH and 0 <= ox < OW) else torch.zeros(16)
+                        rec = ((lc & 7) * 2) * L1_PLANE + lr * GP + (lc >> 3)
+                        sL1[rec * 8:rec * 8 + 8] = v[:8].to(torch.bfloat16)
+                        sL1[(rec + L1_PLANE) * 8:(rec + L1_PLANE) * 8 + 8] = v[8:].to(torch.bfloat16)
+    # layer 2
+    acc = torch.zeros(128, 64)
+    for ky in range(5):
+        for j in range(12):
+            acc += _mma(sL1, (((j & 7) * 2) * L1_PLANE + ky * GP + (j >> 3)) * 16, L1_PLANE * 16,
+                        wmem, W2_OFF + ky * 2 * STRIP + (12 - j) * BLK, STRIP)
+    for row in range(128):
+        yr, xg = divmod(row, GP)
+        for delta in range(8):
+            oy, ox = Y0 - 2 + yr, X0 - 2 + 8 * xg + delta
+            v = _lrelu(acc[row, delta * 8:delta * 8 + 8] * s2 + b2) if (0 <= oy < OH and 0 <= ox < OW) else torch.zeros(8)
+            rec = delta * L2_PLANE + row
+            sL2[rec * 8:rec * 8 + 8] = v.to(torch.bfloat16)
+    # layer 3
+    acc = torch.zeros(128, 64)
+    for kp in range(3):
+        for j in range(12):
+            acc += _mma(sL2, ((j & 7) * L2_PLANE + 2 * kp * GP + (j >> 3)) * 16, GP * 16,
+                        wmem, W3_OFF + 2 * kp * STRIP + (12 - j) * BLK, STRIP)
+    for row in range(128):
+        yr, xg = divmod(row, GP)
+        for delta in range(8):
+            oy, ox = Y0 + yr, X0 + 8 * xg + delta
+            if yr < TOY and xg < TOX // 8 and oy < OH and ox < OW:
+                out[n, :, oy, ox] = torch.relu(acc[row, delta * 8:delta * 8 + 3] + b3)
 
 
 def test_weight_pack_and_index_plan_replay():
@@ -96,7 +107,7 @@ def test_weight_pack_and_index_plan_replay():
     m.eval()
     import forge_b200._lib as L
     pack = ops.pack_decoder_tc_weights(m.conv_rgb)
-    assert pack.dtype == torch.uint8 and pack.numel() == L.load().forge_decoder_tc_wpack_bytes() == PRM_OFF + 256
+    assert pack.dtype == torch.uint8 and pack.numel() == L.load().forge_decoder_tc_wpack_bytes() == PRM_OFF + 256 == 47360
     Sh, Sw = 12, 20                                     # 24 x 40 output: 2 x 2 tiles, ragged in both directions
     x = torch.randn(1, Sh, Sw, 16)
     out = torch.full((1, 3, 2 * Sh, 2 * Sw), float('nan'))
@@ -122,12 +133,3 @@ def test_weight_pack_and_index_plan_replay():
     scale = max(1.0, ref.abs().max().item())
     assert (out - ref).abs().max().item() <= 4e-3 * scale
     assert (out - ref32).abs().max().item() <= 6e-2 * scale
-
-
-def test_tap_pairs_cover_the_5x5_filter_once():
-    seen = []
-    for ta, tb in ops.decoder_tc_taps3():
-        seen.append(ta)
-        if tb is not None:
-            seen.append(tb)
-    assert sorted(seen) == [(ky, kx) for ky in range(5) for kx in range(5)]

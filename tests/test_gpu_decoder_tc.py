@@ -31,12 +31,13 @@ def _probe_expected(img_bf16, off, lbo, sbo, rows):
 
 PROBE_CASES = [
     # (a_off, a_lbo, a_sbo)                    what the decoder needs
-    (0, 2048, 128),                           # aligned start, planes 2 KiB apart
-    (16, 2048, 128),                          # start shifted by one pixel (16 B): a filter tap
-    (16 * 45, 6912, 128),                     # layer-1 geometry: tap (2, 1) on pitch 22, plane stride 432 px
-    (16 * 164, 17024, 128),                   # layer-2 geometry: tap (4, 4) on pitch 40, plane stride 1064 px
-    (16 * 83, 640, 128),                      # layer-3: second K half = the pixel one row down (LBO = 40 px)
-    (16 * 164, 16, 128),                      # layer-3: second K half = the next pixel (LBO = 16 B)
+    (0, 2048, 128),                           # aligned start, K halves 2 KiB apart
+    (16, 2048, 128),                          # start shifted by one record (16 B): a filter tap
+    (16 * 45, 6912, 128),                     # layer 1: tap (2, 1) on pitch 22, channel-chunk planes 432 records apart
+    (16 * (6 * 152 + 21), 2432, 128),         # layer 2: phase plane 3, ky = 4, group shift 1, chunk planes 152 records apart
+    (16 * (5 * 160 + 11), 80, 128),           # layer 3: second K half = one row down (LBO = 5 records = 80 B)
+    (16 * 164, 16, 128),                      # K halves overlapping by all but one record (LBO = 16 B)
+    (128 * 5, 1664, 128),                     # a weight-strip window: start at block 5, next strip 13 blocks on
 ]
 
 
