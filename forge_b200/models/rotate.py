@@ -3,8 +3,8 @@
 Same constructor, ``forward(voxels, camPoses_cv2, grid_size)`` signature, parameters
 (``conv3d_1..4``, unused by the live path but present in checkpoints) and plain-attribute grid
 tables.  The materialised grid + matmul + ``F.grid_sample`` + ``torch.cat`` (reference :127-141)
-are one CUDA launch (``forge_rotate_fwd/bwd``); ``T = pose_0 @ inverse(pose_1)`` stays a
-differentiable [M,4,4] torch expression so gradients reach the camera poses.
+are one CUDA launch (``forge_rotate_fwd/bwd``); ``T = pose_0 @ inverse(pose_1)`` is one more small
+launch (``forge_pose_affine_fwd``, differentiable so gradients reach the camera poses).
 """
 import torch
 import torch.nn as nn
@@ -116,13 +116,9 @@ class Rotate_world(nn.Module):
         if grid_size != D:
             gmax = self._compute_axis(grid_size)[1]
 
-        T = self.get_transformation(camPoses_cv2.to(device))                 # [B*(t-1),4,4]
-        A = T.new_zeros(B, t, 3, 4)
-        A[:, 0, 0, 0] = A[:, 0, 1, 1] = A[:, 0, 2, 2] = 1.0                  # view 0: identity (unused, copy job)
-        A[:, 1:] = T.reshape(B, t - 1, 4, 4)[:, :, :3, :]
-        A = A.reshape(B * t, 12)
+        A = ops.pose_affine(camPoses_cv2.to(device))                         # [B*t,12]; view 0: identity (copy job)
         jobs = self._jobs(B, t, device, order)
 
         vox_cl = ops.to_channels_last(voxels.reshape(B * t, C, D, H, W))
-        out_cl = ops.rotate_resample(vox_cl, A.float(), jobs, gx, gy, gz, gmax, B * t)
+        out_cl = ops.rotate_resample(vox_cl, A, jobs, gx, gy, gz, gmax, B * t)
         return out_cl.view(B, t, D, H, W, C).permute(0, 1, 5, 2, 3, 4)

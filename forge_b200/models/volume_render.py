@@ -3,8 +3,8 @@
 Same constructor, ``forward`` / ``proj_origin`` signatures, return-tuple ordering, ``conv_rgb``
 state_dict keys and in-place halving of the caller's ``K``.  The PyTorch3D camera conversion,
 ray sampler, volume sampler and emission-absorption raymarcher (reference :53-63) are replaced
-by one fused CUDA kernel (``forge_raymarch_fwd/bwd``); the camera algebra that feeds it is a
-dozen tiny differentiable torch ops on [N,3,3] tensors, so gradients reach R, T and K.
+by one fused CUDA kernel (``forge_raymarch_fwd/bwd``); the camera algebra that feeds it is one more
+small launch (``forge_camera_prep_fwd/bwd``), differentiable so gradients reach R, T and K.
 """
 import torch
 import torch.nn as nn
@@ -14,7 +14,8 @@ from .. import ops
 
 
 def camera_to_cam12(R, T, K_half, vol_dhw, volume_size):
-    """OpenCV extrinsics/intrinsics -> the 12 floats per view the raymarcher consumes.
+    """OpenCV extrinsics/intrinsics -> the 12 floats per view the raymarcher consumes (torch statement of what
+    ``forge_camera_prep_fwd`` computes in one launch; kept as the differentiable cross-check of that kernel).
 
     Volume-local sample point of pixel (i, j) at depth z:  o + z * M [j+0.5, i+0.5, 1]^T with
       o = -R^T t / s,   M = diag(1/s) R^T K^-1,   s_axis = (size_axis - 1)/2 * volume_size / D
@@ -68,6 +69,7 @@ class VolRender(nn.Module):
             nn.Conv2d(8, 3, kernel_size=self.k_size, stride=1, padding=self.pad_size),
         )
         self._zs = {}
+        self._vidx = {}
         # decoder arithmetic: None = fp32 like the reference; torch.bfloat16 = bf16 operands / fp32 accumulation on
         # the tensor cores (BASELINE.json configs[2] "bf16 decoder"; RGB then deviates ~1e-2, not 1e-4): the
         # tcgen05 kernel in eval mode, cuDNN under autocast in training mode
@@ -95,10 +97,9 @@ class VolRender(nn.Module):
         camera_params['K'][:, -1, -1] = 1.0
         return camera_params['K']
 
-    def render_features(self, camera_params, feature_3d, density_3d, render_depth=False, view2vol=None):
-        """The part of ``forward`` PyTorch3D used to do: -> (feat [N,S,S,16], sil [N,S,S], depth|None,
-        R, T, K_half on the volume's device).  ``view2vol`` (int [N]) lets the caller pass V distinct
-        volumes instead of one materialised copy per view (reference models/model.py:138-139)."""
+    def _render(self, camera_params, feature_3d, density_3d, render_depth, view2vol):
+        """-> (feat [N,S,S,16], sil [N,S,S], depth|None, origin_proj [N,2], R, T, K_half): one camera-prep launch,
+        the volume pack and the raymarch."""
         if not feature_3d.is_cuda:
             raise RuntimeError("forge_b200.VolRender needs CUDA volumes; there is no CPU path")
         device = feature_3d.device
@@ -111,16 +112,30 @@ class VolRender(nn.Module):
                 raise ValueError("Input volumes have to have the same batch size as rays.")
             if N > 1 and feature_3d.stride(0) == 0 and density_3d.stride(0) == 0:   # expand()-ed single volume
                 feature_3d, density_3d = feature_3d[:1], density_3d[:1]
-                view2vol = torch.zeros(N, dtype=torch.int32, device=device)
+                view2vol = self._view_index(N, device, zeros=True)
             else:
-                view2vol = torch.arange(N, dtype=torch.int32, device=device)
+                view2vol = self._view_index(N, device, zeros=False)
         else:
             view2vol = view2vol.to(device=device, dtype=torch.int32)
         _, C, D, H, W = feature_3d.shape
-        cam12 = camera_to_cam12(R.float(), T.float(), K.float(), (D, H, W), self.volume_physical_size)
+        cam12, oproj = ops.camera_prep(R, T, K, (D, H, W), self.volume_physical_size)
         S = self.img_size // 2
         feat, sil, depth = ops.raymarch(feature_3d, density_3d, cam12, view2vol, self._depths(device), S, S,
                                         render_depth)
+        return feat, sil, depth, oproj, R, T, K
+
+    def _view_index(self, N, device, zeros):
+        key = (N, str(device), zeros)
+        if key not in self._vidx:
+            self._vidx[key] = (torch.zeros(N, dtype=torch.int32, device=device) if zeros
+                               else torch.arange(N, dtype=torch.int32, device=device))
+        return self._vidx[key]
+
+    def render_features(self, camera_params, feature_3d, density_3d, render_depth=False, view2vol=None):
+        """The part of ``forward`` PyTorch3D used to do: -> (feat [N,S,S,16], sil [N,S,S], depth|None,
+        R, T, K_half on the volume's device).  ``view2vol`` (int [N]) lets the caller pass V distinct
+        volumes instead of one materialised copy per view (reference models/model.py:138-139)."""
+        feat, sil, depth, _, R, T, K = self._render(camera_params, feature_3d, density_3d, render_depth, view2vol)
         return feat, sil, depth, R, T, K
 
     def forward(self, camera_params, feature_3d, density_3d, render_depth=False, return_origin_proj=False,
@@ -130,14 +145,14 @@ class VolRender(nn.Module):
         feature_3d: [B,C,D,H,W]
         density_3d: [B,1,D,H,W]
         '''
-        feat, sil, depth, R, T, K = self.render_features(camera_params, feature_3d, density_3d, render_depth, view2vol)
+        feat, sil, depth, origin_proj, _, _, _ = self._render(camera_params, feature_3d, density_3d, render_depth,
+                                                              view2vol)
         rendered_imgs = self.decode(feat)
         rendered_silhouettes = F.interpolate(sil.unsqueeze(1), size=[self.img_size] * 2, mode='bilinear')
         if render_depth:
             rendered_depth = F.interpolate(depth.unsqueeze(1), size=[self.img_size] * 2, mode='bilinear')
 
         if return_origin_proj:
-            origin_proj = origin_projection(T.float(), K.float())
             if render_depth:
                 return rendered_imgs, rendered_silhouettes, rendered_depth, origin_proj
             else:

@@ -366,3 +366,82 @@ def umma_probe(image_u8, a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo):
         _lib.call("forge_umma_probe", _ptr(image_u8), image_u8.numel(), a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo,
                   _ptr(out), _stream(image_u8))
     return out
+
+
+# ---- camera / pose algebra -------------------------------------------------------------------------
+class _CameraPrep(torch.autograd.Function):
+    """(R [N,3,3], T [N,3], K_half [N,3,3]) -> cam12 [N,12], origin_proj [N,2]; one launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, R, T, K_half, scale, eps):
+        N = R.shape[0]
+        cam12 = torch.empty(N, 12, dtype=torch.float32, device=R.device)
+        oproj = torch.empty(N, 2, dtype=torch.float32, device=R.device)
+        with torch.cuda.device(R.device):
+            _lib.call("forge_camera_prep_fwd", _ptr(R), _ptr(T), _ptr(K_half), N, scale[0], scale[1], scale[2], eps,
+                      _ptr(cam12), _ptr(oproj), _stream(R))
+        ctx.save_for_backward(R, T, K_half)
+        ctx.scale, ctx.eps = scale, eps
+        return cam12, oproj
+
+    @staticmethod
+    def backward(ctx, g_cam12, g_oproj):
+        R, T, K_half = ctx.saved_tensors
+        N = R.shape[0]
+        need = ctx.needs_input_grad
+        gR = torch.empty_like(R) if need[0] else None
+        gT = torch.empty_like(T) if need[1] else None
+        gK = torch.empty_like(K_half) if need[2] else None
+        if any(need[:3]):
+            gc = None if g_cam12 is None else _f32c(g_cam12)
+            go = None if g_oproj is None else _f32c(g_oproj)
+            with torch.cuda.device(R.device):
+                _lib.call("forge_camera_prep_bwd", _ptr(R), _ptr(T), _ptr(K_half), N, ctx.scale[0], ctx.scale[1],
+                          ctx.scale[2], ctx.eps, _ptr(gc), _ptr(go), _ptr(gR), _ptr(gT), _ptr(gK), _stream(R))
+        return gR, gT, gK, None, None
+
+
+def camera_prep(R, T, K_half, vol_dhw, volume_size, eps=1e-6):
+    """OpenCV extrinsics / halved intrinsics -> (cam12 [N,12] for the raymarcher, origin_proj [N,2]); differentiable
+    w.r.t. R, T and fx, fy, cx, cy.  Reference models/volume_render.py:53-61, :77-83."""
+    _require_cuda(R, T, K_half)
+    D, H, W = vol_dhw
+    vs = float(volume_size) / D
+    scale = ((W - 1) * 0.5 * vs, (H - 1) * 0.5 * vs, (D - 1) * 0.5 * vs)
+    return _CameraPrep.apply(_f32c(R), _f32c(T), _f32c(K_half), scale, float(eps))
+
+
+class _PoseAffine(torch.autograd.Function):
+    """poses [B,t,4,4] -> affine12 [B*t,12] (view 0: identity); backward with three small batched matmuls."""
+
+    @staticmethod
+    def forward(ctx, poses):
+        B, t = poses.shape[:2]
+        A = torch.empty(B * t, 12, dtype=torch.float32, device=poses.device)
+        need = ctx.needs_input_grad[0]
+        pinv = torch.empty(B, t, 4, 4, dtype=torch.float32, device=poses.device) if need else None
+        with torch.cuda.device(poses.device):
+            _lib.call("forge_pose_affine_fwd", _ptr(poses), B, t, _ptr(A), _ptr(pinv), None, _stream(poses))
+        if need:
+            ctx.save_for_backward(poses, pinv)
+        return A
+
+    @staticmethod
+    def backward(ctx, gA):
+        poses, X = ctx.saved_tensors                       # X = inverse(poses)
+        B, t = poses.shape[:2]
+        G = torch.zeros(B, t, 4, 4, dtype=torch.float32, device=poses.device)
+        G[:, 1:, :3, :] = gA.reshape(B, t, 3, 4)[:, 1:]    # T = P0 X_v for v >= 1; the identity row is a constant
+        Xt = X.transpose(-1, -2)
+        gP = -(Xt @ (poses[:, :1].transpose(-1, -2) @ G) @ Xt)          # dL/dP_v = -X^T (P0^T G) X^T
+        gP[:, 0] = (G @ Xt).sum(dim=1)                                  # dL/dP_0 = sum_v G_v X_v^T  (G_0 = 0)
+        return gP
+
+
+def pose_affine(camPoses):
+    """camPoses [B,t,4,4] -> [B*t,12]: rows of pose_0 @ inverse(pose_v) (reference models/rotate.py:64-89), identity for
+    v = 0, in one launch (differentiable)."""
+    _require_cuda(camPoses)
+    if camPoses.dim() != 4 or camPoses.shape[-2:] != (4, 4):
+        raise ValueError("camPoses_cv2 must be [B,t,4,4] (got %s)" % (tuple(camPoses.shape),))
+    return _PoseAffine.apply(_f32c(camPoses))

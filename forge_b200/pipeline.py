@@ -18,8 +18,7 @@ nothing is cached across steps.
 """
 import torch
 
-from . import ops, _lib
-from .models.volume_render import camera_to_cam12
+from . import _lib
 
 
 class _Slot:
@@ -30,6 +29,7 @@ class _Slot:
         self.T = torch.empty(N, 3, device=dev)
         self.K = torch.empty(N, 3, 3, device=dev)
         self.view2vol = torch.empty(N, dtype=torch.int32, device=dev)
+        self.cam12 = torch.empty(N, 12, device=dev)
         self.feat_pad = torch.empty(V, D + 2, D + 2, D + 2, 16, device=dev)
         self.dens_quad = torch.empty(V, D + 2, D + 1, D + 1, 4, device=dev)
         self.out = torch.empty(N, S, S, 16, device=dev)
@@ -70,16 +70,18 @@ class StreamedRenderer:
             s.copied_in.record(self.s_in)
         with torch.cuda.stream(self.s_cmp), torch.no_grad():
             self.s_cmp.wait_event(s.copied_in)
-            Kh = s.K / 2.0
-            Kh[:, 2, 2] = 1.0
-            cam12 = camera_to_cam12(s.R, s.T, Kh, (self.D, self.D, self.D), self.m.volume_physical_size).contiguous()
+            s.K.mul_(0.5)                       # the device copy is halved, like VolRender.forward does to its argument
             st = self.s_cmp.cuda_stream
+            vs = self.m.volume_physical_size / self.D
+            sc = (self.D - 1) * 0.5 * vs
+            _lib.call("forge_camera_prep_fwd", s.R.data_ptr(), s.T.data_ptr(), s.K.data_ptr(), self.N, sc, sc, sc, 1e-6,
+                      s.cam12.data_ptr(), None, st)
             _lib.call("forge_pack_volume", s.feat.data_ptr(), 0, s.dens.data_ptr(), s.feat_pad.data_ptr(),
                       s.dens_quad.data_ptr(), self.V, self.D, self.D, self.D, st)
             _lib.call("forge_raymarch_fwd", s.feat_pad.data_ptr(), s.dens_quad.data_ptr(), s.view2vol.data_ptr(),
-                      cam12.data_ptr(), self.zs.data_ptr(), s.out.data_ptr(), s.sil.data_ptr(), s.depth.data_ptr(),
+                      s.cam12.data_ptr(), self.zs.data_ptr(), s.out.data_ptr(), s.sil.data_ptr(), s.depth.data_ptr(),
                       self.N, self.V, self.D, self.D, self.D, self.S, self.S, self.zs.numel(), st)
-            self.launches += 2
+            self.launches += 3
             s.computed.record(self.s_cmp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(s.computed)

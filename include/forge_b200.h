@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 8
+#define FORGE_ABI_VERSION 9
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -143,6 +143,29 @@ int forge_rotate_bwd(const float* vox_cl, const float* affine12, const int* jobs
                      const float* gy, const float* gz, float grid_coord_max, const float* g_out_cl,
                      float* grad_vox_cl, float* grad_affine12, int M, int C, int D, int H, int W,
                      void* stream);
+
+/* ---- camera / pose algebra (host-glue kernels, one launch each) -----------------------------
+ * forge_camera_prep_fwd replaces cameras_from_opencv_projection + the NDC un-projection + Volumes.world_to_local
+ * that models/volume_render.py:53-61 runs through PyTorch3D, and transform_points_screen(0) of :77-83 / :97-103:
+ *   R [N][3][3], T [N][3], K_half [N][3][3] (OpenCV, intrinsics already halved; only fx, fy, cx, cy are read)
+ *   s = ((W-1)/2, (H-1)/2, (D-1)/2) * volume_size / D        (sx, sy, sz)
+ *   cam12[n] = { o = -R^T t / s,  M = diag(1/s) R^T K^-1 }     sample point of pixel (i, j) at depth z: o + z M (j+.5, i+.5, 1)^T
+ *   origin_proj[n] = (fx tx / tz + cx, fy ty / tz + cy), |tz| clamped to eps with its sign kept; may be NULL.
+ * forge_camera_prep_bwd: gradients of both outputs w.r.t. R, T, K_half (each output / gradient pointer may be NULL;
+ * grad_K is written densely, zeros outside fx, fy, cx, cy). */
+int forge_camera_prep_fwd(const float* R, const float* T, const float* K_half, int N, float sx, float sy, float sz,
+                          float eps, float* cam12, float* origin_proj, void* stream);
+int forge_camera_prep_bwd(const float* R, const float* T, const float* K_half, int N, float sx, float sy, float sz,
+                          float eps, const float* g_cam12, const float* g_origin_proj, float* grad_R, float* grad_T,
+                          float* grad_K, void* stream);
+
+/* forge_pose_affine_fwd replaces Rotate_world.get_transformation (models/rotate.py:64-89: repeat, reshape,
+ * torch.inverse, matmul) and the identity row of the passthrough view:
+ *   poses [B][t][4][4] camera-to-world; affine12[b*t + v] = (poses[b][0] @ inverse(poses[b][v]))[:3, :] for v >= 1,
+ *   identity for v = 0; pose_inv [B*t][4][4] (optional) receives inverse(poses) for the backward pass;
+ *   *singular_flag (optional, device int) is set to 1 when a pose is singular (its outputs are NaN). */
+int forge_pose_affine_fwd(const float* poses, int B, int t, float* affine12, float* pose_inv, int* singular_flag,
+                          void* stream);
 
 /* ---- test hook: the index path of both samplers -------------------------------------------
  * For each normalised point pts[m] = (x, y, z) returns the base voxel (floor) index base[m] =
