@@ -28,8 +28,9 @@
 //            down; B: LBO = one strip): 1 M-tile x 3 ky-pairs x 12 columns = 36 MMAs, N = 64 =
 //            (delta, co padded to 8).
 //
-// Epilogues (tcgen05.ld, one accumulator row per thread, the two warp groups split the columns)
-// apply scale/shift (folded BN + bias), LeakyReLU, the zero padding of the next convolution, and
+// The BN scales are folded into the bf16 weights; epilogues (tcgen05.ld, one accumulator row per
+// thread, the two warp groups split the columns) add the shift (folded BN + bias), apply
+// LeakyReLU and the zero padding of the next convolution, and
 // write bf16 phase planes for the next layer; the last one applies ReLU and stores fp32 NCHW as
 // float4.  Weights (46 KB of prebuilt B tiles / strips) arrive by one bulk async copy (TMA engine).
 // Persistent CTAs, 2 per SM (104 KB smem, 256 TMEM columns each).
@@ -41,9 +42,9 @@ namespace forge {
 namespace dtc {
 
 constexpr int kThreads = 256;
-constexpr int TOX = 32, TOY = 16;                 // output tile
-constexpr int IN_W = TOX / 2 + 6, IN_H = TOY / 2 + 6;     // 22 x 14 input pixels (pitch 22)
-constexpr int L1_W = TOX + 8;                     // 40 x 24 layer-1 pixels = 5 groups of 8 per row
+constexpr int TOX = 32, TOY = 20;                 // output tile (20 rows: layer 2 fills 120 of its 128 MMA rows)
+constexpr int IN_W = TOX / 2 + 6, IN_H = TOY / 2 + 6;     // 22 x 16 input pixels (pitch 22)
+constexpr int L1_W = TOX + 8;                     // 40 x 28 layer-1 pixels = 5 groups of 8 per row
 constexpr int GP = L1_W / 8;                      // record pitch of the phase planes (groups per row)
 constexpr int M1_TILES = 3;                       // 128-row tiles of flattened input pixels in layer 1
 constexpr int IN_PLANE = 432;                     // records per input channel-chunk plane >= 3*128 + 2*22 + 2
@@ -51,6 +52,7 @@ constexpr int L1_PLANE = 152;                     // records per layer-1 plane >
 constexpr int L2_PLANE = 160;                     // records per layer-2 plane >= 128 + 5*5 + 1
 static_assert(L1_W % 8 == 0 && GP == 5, "phase planes assume 8-pixel groups");
 static_assert(IN_PLANE >= M1_TILES * 128 + 2 * IN_W + 2, "input plane too small for the flattened over-read");
+static_assert(IN_H * IN_W <= IN_PLANE && (TOY + 8) * GP <= L1_PLANE && (TOY + 4) * GP <= L2_PLANE && TOY % 2 == 0, "planes too small for the tile");
 static_assert(L1_PLANE >= 128 + 4 * GP + 1 && L2_PLANE >= 128 + 5 * GP + 1, "phase plane too small for the over-read");
 static_assert((TOY / 2 + 4) * IN_W <= M1_TILES * 128 && (TOY + 4) * GP <= 128 && TOY * GP <= 128, "M tiles do not cover the layer");
 
@@ -62,7 +64,7 @@ constexpr int W1_OFF = 0, W2_OFF = W1_OFF + 9 * W1_TILE, W3_OFF = W2_OFF + 10 * 
 constexpr int WPACK_BYTES = PRM_OFF + 256;        // 47360
 // the input planes alias the layer-2 planes: the former are dead once layer 1's MMAs have completed
 constexpr int SM_W = 0, SM_L1 = SM_W + WPACK_BYTES, SM_L2 = SM_L1 + 16 * L1_PLANE * 16, SM_IN = SM_L2,
-              SM_BAR = SM_L2 + 8 * L2_PLANE * 16, SM_TOTAL = SM_BAR + 32;
+              SM_BAR = SM_L2 + 8 * L2_PLANE * 16, SM_TOTAL = SM_BAR + 64;
 static_assert(2 * IN_PLANE * 16 <= 8 * L2_PLANE * 16, "input planes must fit in the layer-2 region they alias");
 constexpr int TMEM_COLS = 256;                    // layer 1: 3 x 64 columns, layer 2: 64 (192..255), layer 3: 64 (0..63)
 
@@ -153,6 +155,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : 0.01f * v; }
 
+// input tile: IN_H * IN_W pixels x 2 channel halves = 704 (pixel, half) items, 3 per thread (the last one partial)
+constexpr int P0_ITEMS = IN_H * IN_W * 2, P0_PER_THREAD = (P0_ITEMS + kThreads - 1) / kThreads;
+
+__device__ __forceinline__ const float4* p0_src(const float4* xin, int e, int iy0, int ix0, int Sh, int Sw) {
+    const int px = e >> 1, half = e & 1;
+    const int r = px / IN_W, c = px - r * IN_W;
+    const int iy = iy0 + r, ix = ix0 + c;
+    if (e >= P0_ITEMS || iy < 0 || iy >= Sh || ix < 0 || ix >= Sw) return nullptr;
+    return xin + (static_cast<long long>(iy) * Sw + ix) * 4 + half * 2;
+}
+
+// (acc + bias) -> LeakyReLU(0.01) -> bf16 pair; max(v, 0.01 v) is LeakyReLU for a slope below 1
+__device__ __forceinline__ uint32_t act_pack(float a0, float a1, float b0, float b1) {
+    const float v0 = a0 + b0, v1 = a1 + b1;
+    return pack_bf16(fmaxf(v0, 0.01f * v0), fmaxf(v1, 0.01f * v1));
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__ wpack, float* __restrict__ rgb, int Sh,
                   int Sw, int tiles_x, int tiles_y, int total_tiles) {
@@ -162,9 +181,9 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
     unsigned char* sL1 = smem + SM_L1;
     unsigned char* sL2 = smem + SM_L2;
     unsigned long long* wbar = reinterpret_cast<unsigned long long*>(smem + SM_BAR);
-    unsigned long long* mbar = wbar + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16);
-    const float* prm = reinterpret_cast<const float*>(sW + PRM_OFF);      // s1[16] b1[16] s2[8] b2[8] b3[4]
+    unsigned long long* mbar = wbar + 1;                                  // [0..2]: layer-1 M-tiles, [3]: layer 2, [4]: layer 3
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 48);
+    const float4* prm4 = reinterpret_cast<const float4*>(sW + PRM_OFF);   // b1[16] b2[8] b3[4]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int OH = 2 * Sh, OW = 2 * Sw;
@@ -172,7 +191,8 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
     // ---- one-time setup: barriers, weights (bulk async copy), TMEM, zeroed activation planes ----
     if (tid == 0) {
         mbar_init(wbar, 1);
-        mbar_init(mbar, 1);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) mbar_init(mbar + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -199,68 +219,92 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
         const int tyi = t2 / tiles_x, txi = t2 - tyi * tiles_x;
         const int Y0 = tyi * TOY, X0 = txi * TOX;
 
-        // ---- P0: input tile fp32 NHWC -> two bf16 channel-chunk planes (zeros outside the image) ----
+        // ---- P0: input tile fp32 NHWC -> two bf16 channel-chunk planes (zeros outside the image); all of a
+        //      thread's loads are issued before the first use ----
         {
             const int iy0 = Y0 / 2 - 3, ix0 = X0 / 2 - 3;
             const float4* xin = reinterpret_cast<const float4*>(x) + static_cast<long long>(n) * Sh * Sw * 4;
-            for (int e = tid; e < IN_H * IN_W * 2; e += kThreads) {
-                const int px = e >> 1, half = e & 1;
-                const int r = px / IN_W, c = px - r * IN_W;
-                const int iy = iy0 + r, ix = ix0 + c;
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (iy >= 0 && iy < Sh && ix >= 0 && ix < Sw) {
-                    const float4* p = xin + (static_cast<long long>(iy) * Sw + ix) * 4 + half * 2;
-                    v0 = __ldg(p);
-                    v1 = __ldg(p + 1);
+            float4 v[P0_PER_THREAD][2];
+#pragma unroll
+            for (int k = 0; k < P0_PER_THREAD; ++k) {
+                const float4* p = p0_src(xin, tid + k * kThreads, iy0, ix0, Sh, Sw);
+                v[k][0] = v[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p) {
+                    v[k][0] = __ldg(p);
+                    v[k][1] = __ldg(p + 1);
                 }
-                *reinterpret_cast<uint4*>(sIn + (half * IN_PLANE + px) * 16) =
-                    make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+            }
+#pragma unroll
+            for (int k = 0; k < P0_PER_THREAD; ++k) {
+                const int e = tid + k * kThreads;
+                if (e < P0_ITEMS)
+                    *reinterpret_cast<uint4*>(sIn + ((e & 1) * IN_PLANE + (e >> 1)) * 16) =
+                        make_uint4(pack_bf16(v[k][0].x, v[k][0].y), pack_bf16(v[k][0].z, v[k][0].w),
+                                   pack_bf16(v[k][1].x, v[k][1].y), pack_bf16(v[k][1].z, v[k][1].w));
             }
         }
         proxy_fence();
         tc_fence_before();
         __syncthreads();
 
-        // ---- P1: transposed conv: 3 M-tiles x 9 input shifts, N = (parity class, co) ----
+        // ---- P1: transposed conv: 3 M-tiles x 9 input shifts, N = (parity class, co); one commit per M-tile so
+        //      that the epilogue of tile j overlaps the MMAs of the tiles behind it ----
         if (warp == 0) {
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
-                for (int j = 0; j < M1_TILES; ++j)
+                for (int j = 0; j < M1_TILES; ++j) {
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const int a = t / 3, b = t - a * 3;       // source pixel offset (rows, cols) inside the input tile
                         umma_bf16(tmem + j * 64, make_desc(aIn + (j * 128 + a * IN_W + b) * 16, IN_PLANE * 16, 128),
                                   make_desc(aW + W1_OFF + t * W1_TILE, 1024, 128), IDESC, t > 0);
                     }
-                umma_commit(mbar);
+                    umma_commit(mbar + j);
+                }
             }
             __syncwarp();
         }
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-        tc_fence_after();
+        // the next tile's input is pulled into L2 while this tile computes
+        {
+            const int nt = tile + gridDim.x;
+            if (nt < total_tiles) {
+                const int nn = nt / (tiles_x * tiles_y), nt2 = nt - nn * tiles_x * tiles_y;
+                const int nty = nt2 / tiles_x, ntx = nt2 - nty * tiles_x;
+                const float4* xin = reinterpret_cast<const float4*>(x) + static_cast<long long>(nn) * Sh * Sw * 4;
+#pragma unroll
+                for (int k = 0; k < P0_PER_THREAD; ++k) {
+                    const float4* p = p0_src(xin, tid + k * kThreads, nty * TOY / 2 - 3, ntx * TOX / 2 - 3, Sh, Sw);
+                    if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
+            }
+        }
+        {
+            const float4 b1a = prm4[0], b1b = prm4[1], b1c = prm4[2], b1d = prm4[3];
 #pragma unroll 1
-        for (int j = 0; j < M1_TILES; ++j) {
-            float acc[32];                                        // classes (py = grp, px = 0) and (py = grp, px = 1)
-            tmem_ld32(t_lane + j * 64, acc);
-            const int m = j * 128 + row, yr = m / IN_W, xr = m - yr * IN_W;
-            if (yr < TOY / 2 + 4 && xr < TOX / 2 + 4) {
-                const int lr = 2 * yr + grp, oy = Y0 - 4 + lr;
+            for (int j = 0; j < M1_TILES; ++j) {
+                mbar_wait(mbar + j, phase);
+                tc_fence_after();
+                float acc[32];                                    // classes (py = grp, px = 0) and (py = grp, px = 1)
+                tmem_ld32(t_lane + j * 64, acc);
+                const int m = j * 128 + row, yr = m / IN_W, xr = m - yr * IN_W;
+                if (yr < TOY / 2 + 4 && xr < TOX / 2 + 4) {
+                    const int lr = 2 * yr + grp, oy = Y0 - 4 + lr;
 #pragma unroll
-                for (int px = 0; px < 2; ++px) {
-                    const int lc = 2 * xr + px, ox = X0 - 4 + lc;
-                    const bool inside = oy >= 0 && oy < OH && ox >= 0 && ox < OW;     // zero padding of layer 2
-                    uint32_t q[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float v0 = inside ? lrelu(fmaf(acc[px * 16 + 2 * c], prm[2 * c], prm[16 + 2 * c])) : 0.f;
-                        const float v1 = inside ? lrelu(fmaf(acc[px * 16 + 2 * c + 1], prm[2 * c + 1], prm[16 + 2 * c + 1])) : 0.f;
-                        q[c] = pack_bf16(v0, v1);
+                    for (int px = 0; px < 2; ++px) {
+                        const int lc = 2 * xr + px, ox = X0 - 4 + lc;
+                        const float* a = acc + px * 16;
+                        uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0;
+                        if (oy >= 0 && oy < OH && ox >= 0 && ox < OW) {       // else: zero padding of layer 2
+                            q0 = make_uint4(act_pack(a[0], a[1], b1a.x, b1a.y), act_pack(a[2], a[3], b1a.z, b1a.w),
+                                            act_pack(a[4], a[5], b1b.x, b1b.y), act_pack(a[6], a[7], b1b.z, b1b.w));
+                            q1 = make_uint4(act_pack(a[8], a[9], b1c.x, b1c.y), act_pack(a[10], a[11], b1c.z, b1c.w),
+                                            act_pack(a[12], a[13], b1d.x, b1d.y), act_pack(a[14], a[15], b1d.z, b1d.w));
+                        }
+                        unsigned char* dst = sL1 + (((lc & 7) * 2) * L1_PLANE + lr * GP + (lc >> 3)) * 16;
+                        *reinterpret_cast<uint4*>(dst) = q0;
+                        *reinterpret_cast<uint4*>(dst + L1_PLANE * 16) = q1;
                     }
-                    unsigned char* dst = sL1 + (((lc & 7) * 2) * L1_PLANE + lr * GP + (lc >> 3)) * 16;
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(q[0], q[1], q[2], q[3]);
-                    *reinterpret_cast<uint4*>(dst + L1_PLANE * 16) = make_uint4(q[4], q[5], q[6], q[7]);
                 }
             }
         }
@@ -279,29 +323,26 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
                         umma_bf16(tmem + 192,
                                   make_desc(aL1 + (((j & 7) * 2) * L1_PLANE + ky * GP + (j >> 3)) * 16, L1_PLANE * 16, 128),
                                   make_desc(aW + W2_OFF + ky * 2 * STRIP + (12 - j) * BLK, STRIP, 128), IDESC, (ky | j) > 0);
-                umma_commit(mbar);
+                umma_commit(mbar + 3);
             }
             __syncwarp();
         }
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-        tc_fence_after();
         {
+            const float4 b2a = prm4[4], b2b = prm4[5];
+            mbar_wait(mbar + 3, phase);
+            tc_fence_after();
             float acc[32];                                        // pixels delta = 4 grp .. 4 grp + 3 of this row's group
             tmem_ld32(t_lane + 192, acc);
             const int yr = row / GP, xg = row - yr * GP, oy = Y0 - 2 + yr;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 const int delta = 4 * grp + d, ox = X0 - 2 + 8 * xg + delta;
-                const bool inside = oy >= 0 && oy < OH && ox >= 0 && ox < OW;         // zero padding of layer 3
-                uint32_t q[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float v0 = inside ? lrelu(fmaf(acc[d * 8 + 2 * c], prm[32 + 2 * c], prm[40 + 2 * c])) : 0.f;
-                    const float v1 = inside ? lrelu(fmaf(acc[d * 8 + 2 * c + 1], prm[32 + 2 * c + 1], prm[40 + 2 * c + 1])) : 0.f;
-                    q[c] = pack_bf16(v0, v1);
-                }
-                *reinterpret_cast<uint4*>(sL2 + (delta * L2_PLANE + row) * 16) = make_uint4(q[0], q[1], q[2], q[3]);
+                const float* a = acc + d * 8;
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (oy >= 0 && oy < OH && ox >= 0 && ox < OW)                  // else: zero padding of layer 3
+                    q = make_uint4(act_pack(a[0], a[1], b2a.x, b2a.y), act_pack(a[2], a[3], b2a.z, b2a.w),
+                                   act_pack(a[4], a[5], b2b.x, b2b.y), act_pack(a[6], a[7], b2b.z, b2b.w));
+                *reinterpret_cast<uint4*>(sL2 + (delta * L2_PLANE + row) * 16) = q;
             }
         }
         proxy_fence();
@@ -318,27 +359,28 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
                     for (int j = 0; j < 12; ++j)
                         umma_bf16(tmem, make_desc(aL2 + ((j & 7) * L2_PLANE + 2 * kp * GP + (j >> 3)) * 16, GP * 16, 128),
                                   make_desc(aW + W3_OFF + 2 * kp * STRIP + (12 - j) * BLK, STRIP, 128), IDESC, (kp | j) > 0);
-                umma_commit(mbar);
+                umma_commit(mbar + 4);
             }
             __syncwarp();
         }
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-        tc_fence_after();
         {
+            const float4 b3 = prm4[6];
+            mbar_wait(mbar + 4, phase);
+            tc_fence_after();
             float acc[32];
             tmem_ld32(t_lane, acc);
             const int yr = row / GP, xg = row - yr * GP;
             const int oy = Y0 + yr, ox = X0 + 8 * xg + 4 * grp;
             if (yr < TOY && xg < TOX / 8 && oy < OH && ox < OW) {
+                const float bias[3] = {b3.x, b3.y, b3.z};
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float b = prm[48 + c];
+                    const float b = bias[c];
                     float* dst = rgb + ((static_cast<long long>(n) * 3 + c) * OH + oy) * OW + ox;
                     const float4 v = make_float4(fmaxf(acc[c] + b, 0.f), fmaxf(acc[8 + c] + b, 0.f), fmaxf(acc[16 + c] + b, 0.f),
                                                  fmaxf(acc[24 + c] + b, 0.f));
                     if (ox + 3 < OW && (OW & 3) == 0) {
-                        *reinterpret_cast<float4*>(dst) = v;
+                        __stcs(reinterpret_cast<float4*>(dst), v);
                     } else {
                         dst[0] = v.x;
                         if (ox + 1 < OW) dst[1] = v.y;
@@ -348,6 +390,7 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
                 }
             }
         }
+        phase ^= 1;                                               // every barrier completed exactly once per tile
         tc_fence_before();
         __syncthreads();
     }

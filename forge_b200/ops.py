@@ -299,11 +299,15 @@ def _strip(w_kx):
 
 def pack_decoder_tc_weights(conv_rgb):
     """Weight pack for forge_decoder_tc_fwd from the reference-shaped ``conv_rgb`` Sequential in eval mode: bf16
-    B operands (9 layer-1 tiles, 10 + 6 strips) followed by the fp32 epilogue constants s1[16] b1[16] s2[8] b2[8]
-    b3[4] (BN scale/shift with the conv bias folded in); layout documented in forge_b200.h."""
+    B operands (9 layer-1 tiles, 10 + 6 strips; the BN scales are folded into the weights) followed by the fp32
+    epilogue shifts b1[16] b2[8] b3[4] (BN shift with the conv bias folded in); layout documented in forge_b200.h."""
     ct, bn1, _, c2, bn2, _, c3 = conv_rgb
     with torch.no_grad():
-        wt, w2, w3 = ct.weight.float(), c2.weight.float(), c3.weight.float()
+        s1 = bn1.weight / torch.sqrt(bn1.running_var + bn1.eps)
+        s2 = bn2.weight / torch.sqrt(bn2.running_var + bn2.eps)
+        wt = ct.weight.float() * s1.view(1, 16, 1, 1)            # [ci, co, ky, kx], BN scale folded before bf16 rounding
+        w2 = c2.weight.float() * s2.view(8, 1, 1, 1)             # [co, ci, ky, kx]
+        w3 = c3.weight.float()
         parts = []
         for a in range(3):                       # layer 1: one [64 = (py, px, co)] x [16 ci] tile per input shift (a, b)
             for b in range(3):
@@ -319,12 +323,10 @@ def pack_decoder_tc_weights(conv_rgb):
         parts.append(wt.new_zeros(13 * 64))
         parts.append(zeros8)
         wb = torch.cat(parts).to(torch.bfloat16).contiguous().view(torch.uint8)
-        s1 = bn1.weight / torch.sqrt(bn1.running_var + bn1.eps)
-        s2 = bn2.weight / torch.sqrt(bn2.running_var + bn2.eps)
-        b1 = (ct.bias - bn1.running_mean) * s1 + bn1.bias
-        b2 = (c2.bias - bn2.running_mean) * s2 + bn2.bias
         prm = torch.zeros(64, dtype=torch.float32, device=wt.device)
-        prm[0:16], prm[16:32], prm[32:40], prm[40:48], prm[48:51] = s1, b1, s2, b2, c3.bias
+        prm[0:16] = (ct.bias - bn1.running_mean) * s1 + bn1.bias
+        prm[16:24] = (c2.bias - bn2.running_mean) * s2 + bn2.bias
+        prm[24:27] = c3.bias
         pack = torch.cat([wb, prm.view(torch.uint8).reshape(-1)]).contiguous()
     assert pack.numel() == _lib.load().forge_decoder_tc_wpack_bytes()
     return pack

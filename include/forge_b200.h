@@ -99,17 +99,18 @@ int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float* rgb_nchw, 
  * Same function as forge_decoder_fwd -- relu(conv_rgb(x)), models/volume_render.py:29-37,73, eval-mode
  * BN -- computed as implicit GEMMs on the 5th-generation tensor cores: the "bf16 decoder" of
  * BASELINE.json configs[2].  Inputs/outputs stay fp32 (x is rounded to bf16 on load, the two hidden
- * activations are rounded to bf16 after BN + LeakyReLU); deviation from the fp32 module ~1e-2.
+ * activations are rounded to bf16 after BN + LeakyReLU); deviation from the fp32 module ~3e-3.
  *   wpack (forge_decoder_tc_wpack_bytes() bytes, 16-byte aligned) = bf16 UMMA B operands built from 8 x 8
  *   core matrices blk[n % 8][k % 8] (128 B, un-swizzled K-major), then the fp32 epilogue constants:
  *     layer 1: 9 tiles (input shift a*3+b) of [k/8 = 2][n = 64][k%8]: n = (py*2+px)*16 + co, k = ci,
- *              value Wt[ci][co][py+4-2a][px+4-2b]
+ *              value Wt[ci][co][py+4-2a][px+4-2b] * s1[co]
  *     layer 2: 10 strips (ky*2 + ci/8) of 13 blocks [8 x zero, W(kx=4), .., W(kx=0)], W(kx)[co][ci%8] =
- *              W2[co][ci][ky][kx]; then 8 zero blocks.  The B operand of source column j (0..11) is the 8-block
+ *              W2[co][ci][ky][kx] * s2[co]; then 8 zero blocks.  The B operand of source column j (0..11) is the 8-block
  *              window starting at block 12-j: block delta holds W(kx = j - delta) or zero.
  *     layer 3: 5 strips (ky) of the same shape with W(kx)[co < 3][ci] = W3[co][ci][ky][kx], one all-zero strip
  *              (the phantom row ky = 5), then 8 zero blocks.
- *     fp32 s1[16] b1[16] s2[8] b2[8] b3[4] (+ padding to 256 B): y = acc * s + b per layer.
+ *     fp32 b1[16] b2[8] b3[4] (+ padding to 256 B): y = acc + b per layer; s = gamma / sqrt(var + eps),
+ *     b1 = (bias_t - mean1) s1 + beta1, b2 likewise, b3 = the last conv's bias.
  *   max_ctas: 0 = two persistent CTAs per SM, otherwise an upper bound on the grid. */
 int forge_decoder_tc_wpack_bytes(void);
 int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, float* rgb_nchw, int N, int S_h, int S_w,
