@@ -187,7 +187,7 @@ def reduce_times(total_ms, e2e_ms, k1_ms, world, device):
 def run_forge(args, rank, world, local_rank):
     import torch.distributed as dist
     from forge_b200 import ops, _lib
-    from forge_b200.models.volume_render import VolRender, camera_to_cam12
+    from forge_b200.models.volume_render import VolRender
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     cfg = make_config()
@@ -198,7 +198,7 @@ def run_forge(args, rank, world, local_rank):
     Kh = inp['K'].clone()
     Kh /= 2.0
     Kh[:, 2, 2] = 1.0
-    cam12 = camera_to_cam12(inp['R'], inp['T'], Kh, (D, D, D), CFG['volume_size']).contiguous()
+    cam12, _ = ops.camera_prep(inp['R'], inp['T'], Kh, (D, D, D), CFG['volume_size'])
     zs = model._depths(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
 
@@ -269,9 +269,7 @@ def run_forge(args, rank, world, local_rank):
         vcl = vox.permute(0, 1, 3, 4, 5, 2).contiguous().reshape(CFG['objects'] * tr, nr, nr, nr, Cr)
         del vox
         gxd, gyd, gzd, gmax = rot._device_axes(nr, nr, nr, dev)
-        A = torch.zeros(CFG['objects'], tr, 3, 4, device=dev)
-        A[:, 1:] = rot.get_transformation(poses).reshape(CFG['objects'], tr - 1, 4, 4)[:, :, :3, :]
-        A = A.reshape(-1, 12).contiguous()
+        A = ops.pose_affine(poses)
         jobs = rot._jobs(CFG['objects'], tr, dev, None)
         out_cl = torch.empty_like(vcl)
         k2_ms = []
@@ -289,6 +287,26 @@ def run_forge(args, rank, world, local_rank):
         k2_avg_ms = sum(k2_ms) / len(k2_ms)
         k2_bytes = 2 * vcl.numel() * 4
         del vcl, out_cl
+
+        # ---- secondary: the tensor-core (bf16, tcgen05) decoder on the raymarcher's output, same run --------------
+        model.decoder_dtype = torch.bfloat16
+        wtc = model._decoder_pack(dev, tc=True)
+        rgb = torch.empty(N, 3, 2 * S, 2 * S, device=dev)
+        dec_ms = []
+        for it in range(3 + 10):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.call("forge_decoder_tc_fwd", o_feat.data_ptr(), wtc.data_ptr(), rgb.data_ptr(), N, S, S, 0,
+                      torch.cuda.current_stream(dev).cuda_stream)
+            b.record()
+            torch.cuda.synchronize(dev)
+            if it >= 3:
+                dec_ms.append(a.elapsed_time(b))
+        dec_avg_ms = sum(dec_ms) / len(dec_ms)
+        dec_flops = 2.0 * 6104 * N * (2 * S) ** 2          # MACs per output pixel: 16*16*9 + 8*16*25 + 3*8*25
+        model.decoder_dtype = None
+        del rgb
 
         # ---- end to end: pinned host inputs -> H2D -> public API -> D2H, everything timed ----------
         h_feat, h_dens = feat.cpu().pin_memory(), dens.cpu().pin_memory()
@@ -380,6 +398,13 @@ def run_forge(args, rank, world, local_rank):
                             "frac": k2_bytes / (k2_avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_kind": peak_kind,
                             "algorithmic_bytes": k2_bytes, "kernel_ms": k2_avg_ms,
                             "note": "secondary line: the HBM-bound kernel of the path, rank 0, timed in the same run"},
+        "roofline_decoder": {"bound": "tensor", "kernel": "decoder_tc_kernel (conv_rgb as tcgen05 implicit GEMMs, bf16 in / fp32 "
+                             "accumulate, %d x 16 x %dx%d -> 3 x %dx%d)" % (N, S, S, 2 * S, 2 * S),
+                             "achieved": dec_flops / (dec_avg_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                             "frac": dec_flops / (dec_avg_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "peak_kind": peak_kind,
+                             "algorithmic_flops": dec_flops, "kernel_ms": dec_avg_ms,
+                             "note": "secondary line: useful conv FLOPs (N = 16/8/3 output channels); the binding unit is the "
+                                     "shared-memory operand path of the MMAs (ncu l1tex__data_pipe_tc_wavefronts 62 %), see DESIGN.md"},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
