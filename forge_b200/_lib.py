@@ -32,10 +32,12 @@ _SIGNATURES = {
     "forge_umma_probe": (_c.c_int, [_F, _I] + [_c.c_uint] * 6 + [_F, _F]),
     "forge_camera_prep_fwd": (_c.c_int, [_F, _F, _F, _I] + [_c.c_float] * 4 + [_F, _F, _F]),
     "forge_camera_prep_bwd": (_c.c_int, [_F, _F, _F, _I] + [_c.c_float] * 4 + [_F] * 5 + [_F]),
+    "forge_upsample2x_fwd": (_c.c_int, [_F, _F, _F, _F, _I, _I, _I, _F]),
+    "forge_upsample2x_bwd": (_c.c_int, [_F, _F, _F, _F, _I, _I, _I, _F]),
     "forge_pose_affine_fwd": (_c.c_int, [_F, _I, _I, _F, _F, _F, _F]),
     "forge_sample_points": (_c.c_int, [_F, _I, _I, _I, _I, _I, _F, _F, _F]),
 }
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _lock = threading.Lock()
 _lib = None

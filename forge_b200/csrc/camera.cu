@@ -227,3 +227,105 @@ extern "C" int forge_pose_affine_fwd(const float* poses, int B, int t, float* af
                                                                                             singular_flag);
     return check_launch(fn);
 }
+
+// ---- x2 bilinear upsample of the silhouette / depth maps ---------------------------------------------
+// F.upsample(mode='bilinear') = interpolate(align_corners=False) of reference models/volume_render.py:69,74 for
+// exactly twice the size: source coordinate max(0.5 (o + 0.5) - 0.5, 0), i.e. weights 0.25 / 0.75 with the
+// borders clamped.  One launch handles up to two maps (silhouette and depth); a thread makes a 2x2 output quad.
+namespace forge {
+
+__global__ void __launch_bounds__(256)
+upsample2x_fwd_kernel(const float* __restrict__ src0, const float* __restrict__ src1, float* __restrict__ dst0,
+                      float* __restrict__ dst1, int M, int Sh, int Sw) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long per_map = static_cast<long long>(M) * Sh * Sw;
+    if (e >= per_map * (src1 ? 2 : 1)) return;
+    const bool second = e >= per_map;
+    const long long r = second ? e - per_map : e;
+    const float* src = second ? src1 : src0;
+    float* dst = second ? dst1 : dst0;
+    const int x = static_cast<int>(r % Sw), y = static_cast<int>((r / Sw) % Sh);
+    const long long m = r / (static_cast<long long>(Sw) * Sh);
+    const float* s = src + m * Sh * Sw;
+    const int xm = max(x - 1, 0), xp = min(x + 1, Sw - 1), ym = max(y - 1, 0), yp = min(y + 1, Sh - 1);
+    const float a = s[ym * Sw + xm], b = s[ym * Sw + x], c = s[ym * Sw + xp];
+    const float d = s[y * Sw + xm], f = s[y * Sw + x], g = s[y * Sw + xp];
+    const float h = s[yp * Sw + xm], i = s[yp * Sw + x], j = s[yp * Sw + xp];
+    // output (2y, 2x): rows (y-1: 0.25, y: 0.75), cols (x-1: 0.25, x: 0.75); at y = 0 / x = 0 the clamp makes both taps equal
+    const float wl0 = x > 0 ? 0.25f : 0.f, wl1 = 1.f - wl0;            // left output column: weights of (x-1, x)
+    const float wr1 = 0.25f, wr0 = 0.75f;                             // right output column: weights of (x, x+1)
+    const float wt0 = y > 0 ? 0.25f : 0.f, wt1 = 1.f - wt0;
+    const float top_l = wl0 * a + wl1 * b, top_r = wr0 * b + wr1 * c;
+    const float mid_l = wl0 * d + wl1 * f, mid_r = wr0 * f + wr1 * g;
+    const float bot_l = wl0 * h + wl1 * i, bot_r = wr0 * i + wr1 * j;
+    float* o = dst + (m * 2 * Sh + 2 * y) * (2 * Sw) + 2 * x;
+    *reinterpret_cast<float2*>(o) = make_float2(wt0 * top_l + wt1 * mid_l, wt0 * top_r + wt1 * mid_r);
+    *reinterpret_cast<float2*>(o + 2 * Sw) = make_float2(0.75f * mid_l + 0.25f * bot_l, 0.75f * mid_r + 0.25f * bot_r);
+}
+
+// adjoint: every source pixel gathers its (up to) 4x4 output neighbourhood with the same weights
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const float* __restrict__ g0, const float* __restrict__ g1, float* __restrict__ gs0,
+                      float* __restrict__ gs1, int M, int Sh, int Sw) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long per_map = static_cast<long long>(M) * Sh * Sw;
+    if (e >= per_map * (g1 ? 2 : 1)) return;
+    const bool second = e >= per_map;
+    const long long r = second ? e - per_map : e;
+    const float* g = second ? g1 : g0;
+    float* gs = second ? gs1 : gs0;
+    const int x = static_cast<int>(r % Sw), y = static_cast<int>((r / Sw) % Sh);
+    const long long m = r / (static_cast<long long>(Sw) * Sh);
+    const float* gm = g + m * 4 * Sh * Sw;
+    const int OW = 2 * Sw, OH = 2 * Sh;
+    // 1-D weights of source index x on output columns 2x-1 .. 2x+2 (clamped taps fold onto the border pixel)
+    float wx[4], wy[4];
+    wx[0] = 0.25f; wx[1] = 0.75f; wx[2] = 0.75f; wx[3] = 0.25f;
+    wy[0] = 0.25f; wy[1] = 0.75f; wy[2] = 0.75f; wy[3] = 0.25f;
+    if (x == 0) { wx[0] = 0.f; wx[1] = 1.f; }
+    if (x == Sw - 1) { wx[3] = 0.f; wx[2] = 1.f; }
+    if (y == 0) { wy[0] = 0.f; wy[1] = 1.f; }
+    if (y == Sh - 1) { wy[3] = 0.f; wy[2] = 1.f; }
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) {
+        const int oy = 2 * y - 1 + dy;
+        if (oy < 0 || oy >= OH) continue;
+        float row = 0.f;
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+            const int ox = 2 * x - 1 + dx;
+            if (ox >= 0 && ox < OW) row = fmaf(wx[dx], gm[static_cast<long long>(oy) * OW + ox], row);
+        }
+        acc = fmaf(wy[dy], row, acc);
+    }
+    gs[r] = acc;
+}
+
+}  // namespace forge
+
+extern "C" int forge_upsample2x_fwd(const float* src0, const float* src1, float* dst0, float* dst1, int M, int S_h, int S_w,
+                                    void* stream) {
+    using namespace forge;
+    const char* fn = "forge_upsample2x_fwd";
+    if (!src0 || !dst0 || (src1 && !dst1)) return fail(fn, "null pointer");
+    if (M <= 0 || S_h <= 0 || S_w <= 0) return fail(fn, "non-positive size");
+    if ((reinterpret_cast<uintptr_t>(dst0) & 7u) || (dst1 && (reinterpret_cast<uintptr_t>(dst1) & 7u)))
+        return fail(fn, "outputs must be 8-byte aligned");
+    const long long total = static_cast<long long>(M) * S_h * S_w * (src1 ? 2 : 1);
+    upsample2x_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src0, src1, dst0, dst1, M, S_h, S_w);
+    return check_launch(fn);
+}
+
+extern "C" int forge_upsample2x_bwd(const float* g_dst0, const float* g_dst1, float* g_src0, float* g_src1, int M, int S_h,
+                                    int S_w, void* stream) {
+    using namespace forge;
+    const char* fn = "forge_upsample2x_bwd";
+    if (!g_dst0 || !g_src0 || (g_dst1 && !g_src1)) return fail(fn, "null pointer");
+    if (M <= 0 || S_h <= 0 || S_w <= 0) return fail(fn, "non-positive size");
+    const long long total = static_cast<long long>(M) * S_h * S_w * (g_dst1 ? 2 : 1);
+    upsample2x_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        g_dst0, g_dst1, g_src0, g_src1, M, S_h, S_w);
+    return check_launch(fn);
+}

@@ -148,9 +148,12 @@ class VolRender(nn.Module):
         feat, sil, depth, origin_proj, _, _, _ = self._render(camera_params, feature_3d, density_3d, render_depth,
                                                               view2vol)
         rendered_imgs = self.decode(feat)
-        rendered_silhouettes = F.interpolate(sil.unsqueeze(1), size=[self.img_size] * 2, mode='bilinear')
-        if render_depth:
-            rendered_depth = F.interpolate(depth.unsqueeze(1), size=[self.img_size] * 2, mode='bilinear')
+        if self.img_size == 2 * sil.shape[-1]:          # exactly x2: both maps in one launch
+            rendered_silhouettes, rendered_depth = ops.upsample2x(sil, depth if render_depth else None)
+        else:
+            rendered_silhouettes = F.interpolate(sil.unsqueeze(1), size=[self.img_size] * 2, mode='bilinear')
+            if render_depth:
+                rendered_depth = F.interpolate(depth.unsqueeze(1), size=[self.img_size] * 2, mode='bilinear')
 
         if return_origin_proj:
             if render_depth:

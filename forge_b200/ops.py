@@ -447,3 +447,42 @@ def pose_affine(camPoses):
     if camPoses.dim() != 4 or camPoses.shape[-2:] != (4, 4):
         raise ValueError("camPoses_cv2 must be [B,t,4,4] (got %s)" % (tuple(camPoses.shape),))
     return _PoseAffine.apply(_f32c(camPoses))
+
+
+# ---- x2 bilinear upsample of the silhouette / depth maps ---------------------------------------------
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        M, Sh, Sw = a.shape
+        oa = torch.empty(M, 1, 2 * Sh, 2 * Sw, dtype=torch.float32, device=a.device)
+        ob = torch.empty_like(oa) if b is not None else None
+        with torch.cuda.device(a.device):
+            _lib.call("forge_upsample2x_fwd", _ptr(a), _ptr(b), _ptr(oa), _ptr(ob), M, Sh, Sw, _stream(a))
+        ctx.dims = (M, Sh, Sw)
+        ctx.two = b is not None
+        if ob is None:
+            ob = torch.empty(0, device=a.device)
+            ctx.mark_non_differentiable(ob)
+        return oa, ob
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        M, Sh, Sw = ctx.dims
+        if ga is None and (gb is None or not ctx.two):
+            return None, None
+        dev = (ga if ga is not None else gb).device
+        ga = torch.zeros(M, 1, 2 * Sh, 2 * Sw, device=dev) if ga is None else _f32c(ga)
+        gb = (torch.zeros_like(ga) if gb is None else _f32c(gb)) if ctx.two else None
+        sa = torch.empty(M, Sh, Sw, dtype=torch.float32, device=dev)
+        sb = torch.empty_like(sa) if ctx.two else None
+        with torch.cuda.device(dev):
+            _lib.call("forge_upsample2x_bwd", _ptr(ga), _ptr(gb), _ptr(sa), _ptr(sb), M, Sh, Sw, _stream(ga))
+        return sa, sb
+
+
+def upsample2x(a, b=None):
+    """[M,S_h,S_w] maps (one or two) -> [M,1,2S_h,2S_w] each, bilinear with align_corners=False (reference
+    models/volume_render.py:69,74: F.upsample to twice the size), both maps in one launch; differentiable."""
+    _require_cuda(a, b)
+    oa, ob = _Upsample2x.apply(_f32c(a), None if b is None else _f32c(b))
+    return oa, (ob if b is not None else None)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 9
+#define FORGE_ABI_VERSION 10
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -159,6 +159,14 @@ int forge_camera_prep_fwd(const float* R, const float* T, const float* K_half, i
 int forge_camera_prep_bwd(const float* R, const float* T, const float* K_half, int N, float sx, float sy, float sz,
                           float eps, const float* g_cam12, const float* g_origin_proj, float* grad_R, float* grad_T,
                           float* grad_K, void* stream);
+
+/* forge_upsample2x_fwd/bwd: F.upsample(mode='bilinear') (align_corners=False) of the silhouette and depth maps to
+ * exactly twice the size (models/volume_render.py:69,74); one launch for one or two maps (src1 / dst1 may be NULL).
+ *   src [M][S_h][S_w] -> dst [M][2 S_h][2 S_w];  bwd writes (does not accumulate) g_src from g_dst. */
+int forge_upsample2x_fwd(const float* src0, const float* src1, float* dst0, float* dst1, int M, int S_h, int S_w,
+                         void* stream);
+int forge_upsample2x_bwd(const float* g_dst0, const float* g_dst1, float* g_src0, float* g_src1, int M, int S_h,
+                         int S_w, void* stream);
 
 /* forge_pose_affine_fwd replaces Rotate_world.get_transformation (models/rotate.py:64-89: repeat, reshape,
  * torch.inverse, matmul) and the identity row of the passthrough view:

@@ -78,3 +78,24 @@ def test_pose_affine_flags_singular_pose():
     poses[0, 1, 2, 2] = 0.0
     A = ops.pose_affine(poses)
     assert torch.isnan(A[1]).all() and torch.isfinite(A[0]).all()
+
+
+@pytest.mark.parametrize("M,Sh,Sw", [(3, 16, 16), (2, 5, 9), (1, 1, 1), (1, 1, 7), (20, 128, 128)])
+def test_upsample2x_matches_interpolate_values_and_grads(M, Sh, Sw):
+    import torch.nn.functional as F
+    torch.manual_seed(M + Sh)
+    a = torch.randn(M, Sh, Sw, device=DEV)
+    b = torch.randn(M, Sh, Sw, device=DEV)
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ak, bk = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ra = F.interpolate(ar.unsqueeze(1), size=[2 * Sh, 2 * Sw], mode='bilinear')
+    rb = F.interpolate(br.unsqueeze(1), size=[2 * Sh, 2 * Sw], mode='bilinear')
+    oa, ob = ops.upsample2x(ak, bk)
+    assert oa.shape == ra.shape and (oa - ra).abs().max().item() <= 1e-6 and (ob - rb).abs().max().item() <= 1e-6
+    wa, wb = torch.randn_like(ra), torch.randn_like(rb)
+    ((ra * wa).sum() + (rb * wb).sum()).backward()
+    ((oa * wa).sum() + (ob * wb).sum()).backward()
+    assert (ak.grad - ar.grad).abs().max().item() <= 1e-5 and (bk.grad - br.grad).abs().max().item() <= 1e-5
+    # single map
+    o1, none = ops.upsample2x(a)
+    assert none is None and torch.equal(o1, oa.detach())
