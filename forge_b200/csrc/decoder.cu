@@ -54,6 +54,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : 0.01f * v; }
 
+// 8 (or 4) output channels += one activation x 8 (4) weights as packed FFMA2 (two fp32 FMAs per instruction on
+// sm_100; per-component rounding identical to fmaf)
+__device__ __forceinline__ void fma8(float2 (&a)[4], float av, const float4& w0, const float4& w1) {
+    const float2 v = make_float2(av, av);
+    a[0] = __ffma2_rn(v, make_float2(w0.x, w0.y), a[0]);
+    a[1] = __ffma2_rn(v, make_float2(w0.z, w0.w), a[1]);
+    a[2] = __ffma2_rn(v, make_float2(w1.x, w1.y), a[2]);
+    a[3] = __ffma2_rn(v, make_float2(w1.z, w1.w), a[3]);
+}
+__device__ __forceinline__ void fma4(float2 (&a)[2], float av, const float4& w) {
+    const float2 v = make_float2(av, av);
+    a[0] = __ffma2_rn(v, make_float2(w.x, w.y), a[0]);
+    a[1] = __ffma2_rn(v, make_float2(w.z, w.w), a[1]);
+}
+__device__ __forceinline__ float get8(const float2 (&a)[4], int co) { return (co & 1) ? a[co >> 1].y : a[co >> 1].x; }
+
 __global__ void __launch_bounds__(kDecThreads, 1)
 decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack, float* __restrict__ rgb, int Sh, int Sw,
                    int tiles_x) {
@@ -103,11 +119,11 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
     if (tid < 480) {
         const int r = tid % 12, g = (tid / 12) % 5, ch = tid / 60;     // ch = class * 2 + half
         const int cls = ch >> 1, half = ch & 1, py = cls >> 1, px = cls & 1;
-        float acc[4][8];
+        float2 acc[4][4];
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int co = 0; co < 8; ++co) acc[p][co] = 0.f;
+            for (int co = 0; co < 4; ++co) acc[p][co] = make_float2(0.f, 0.f);
         const float* wbase = sW1 + cls * 2304 + half * 8;
 #pragma unroll 1
         for (int ty = 0; ty < 3; ++ty) {
@@ -124,17 +140,7 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
                         const float* wp = wbase + ((ty * 3 + tx) * 16 + cq * 4 + cc) * 16;
                         const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            const float av = comp(a[p + 2 - tx], cc);
-                            acc[p][0] = fmaf(av, w0.x, acc[p][0]);
-                            acc[p][1] = fmaf(av, w0.y, acc[p][1]);
-                            acc[p][2] = fmaf(av, w0.z, acc[p][2]);
-                            acc[p][3] = fmaf(av, w0.w, acc[p][3]);
-                            acc[p][4] = fmaf(av, w1.x, acc[p][4]);
-                            acc[p][5] = fmaf(av, w1.y, acc[p][5]);
-                            acc[p][6] = fmaf(av, w1.z, acc[p][6]);
-                            acc[p][7] = fmaf(av, w1.w, acc[p][7]);
-                        }
+                        for (int p = 0; p < 4; ++p) fma8(acc[p], comp(a[p + 2 - tx], cc), w0, w1);
                     }
                 }
             }
@@ -146,7 +152,7 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
             const bool inside = (oy >= 0 && oy < OH && ox >= 0 && ox < OW);     // conv zero padding of layer 2
             float v[8];
 #pragma unroll
-            for (int co = 0; co < 8; ++co) v[co] = inside ? lrelu(acc[p][co] + sB1[half * 8 + co]) : 0.f;
+            for (int co = 0; co < 8; ++co) v[co] = inside ? lrelu(get8(acc[p], co) + sB1[half * 8 + co]) : 0.f;
             float* dst = sL1 + lr * L1_RS + lc * L1_PS + half * 8;
             *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -159,11 +165,11 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
     {
         const bool work = tid < 360;
         const int cih = tid / 180, unit = tid % 180, row = unit % 20, grp = unit / 20;
-        float acc[4][8];
+        float2 acc[4][4];
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int co = 0; co < 8; ++co) acc[p][co] = 0.f;
+            for (int co = 0; co < 4; ++co) acc[p][co] = make_float2(0.f, 0.f);
         if (work) {
 #pragma unroll 1
             for (int ky = 0; ky < 5; ++ky) {
@@ -180,17 +186,7 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
                             const float* wp = sW2 + ((ky * 5 + kx) * 16 + cih * 8 + cq * 4 + cc) * 8;
                             const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll
-                            for (int p = 0; p < 4; ++p) {
-                                const float av = comp(a[p + kx], cc);
-                                acc[p][0] = fmaf(av, w0.x, acc[p][0]);
-                                acc[p][1] = fmaf(av, w0.y, acc[p][1]);
-                                acc[p][2] = fmaf(av, w0.z, acc[p][2]);
-                                acc[p][3] = fmaf(av, w0.w, acc[p][3]);
-                                acc[p][4] = fmaf(av, w1.x, acc[p][4]);
-                                acc[p][5] = fmaf(av, w1.y, acc[p][5]);
-                                acc[p][6] = fmaf(av, w1.z, acc[p][6]);
-                                acc[p][7] = fmaf(av, w1.w, acc[p][7]);
-                            }
+                            for (int p = 0; p < 4; ++p) fma8(acc[p], comp(a[p + kx], cc), w0, w1);
                         }
                     }
                 }
@@ -200,8 +196,8 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
         if (work && cih == 1) {
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-                *reinterpret_cast<float4*>(part + p * 8) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
-                *reinterpret_cast<float4*>(part + p * 8 + 4) = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
+                *reinterpret_cast<float4*>(part + p * 8) = make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y);
+                *reinterpret_cast<float4*>(part + p * 8 + 4) = make_float4(acc[p][2].x, acc[p][2].y, acc[p][3].x, acc[p][3].y);
             }
         }
         __syncthreads();
@@ -215,7 +211,7 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
                 const float o[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
                 float v[8];
 #pragma unroll
-                for (int co = 0; co < 8; ++co) v[co] = inside ? lrelu(acc[p][co] + o[co] + sB2[co]) : 0.f;
+                for (int co = 0; co < 8; ++co) v[co] = inside ? lrelu(get8(acc[p], co) + o[co] + sB2[co]) : 0.f;
                 float* dst = sL2 + row * L2_RS + lc * L2_PS;
                 *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -227,7 +223,7 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
     // ---- phase 3: conv 5x5, 8 -> 3, ReLU, NCHW store; task = (2-px group, row) ----
     if (tid < 256) {
         const int row = tid % 16, grp = tid / 16;
-        float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+        float2 acc[2][2] = {{make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}};
 #pragma unroll 1
         for (int ky = 0; ky < 5; ++ky) {
             const float* l2row = sL2 + (row + ky) * L2_RS + 2 * grp * L2_PS;
@@ -242,12 +238,7 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
                     for (int cc = 0; cc < 4; ++cc) {
                         const float4 w = *reinterpret_cast<const float4*>(sW3 + ((ky * 5 + kx) * 8 + cq * 4 + cc) * 4);
 #pragma unroll
-                        for (int p = 0; p < 2; ++p) {
-                            const float av = comp(a[p + kx], cc);
-                            acc[p][0] = fmaf(av, w.x, acc[p][0]);
-                            acc[p][1] = fmaf(av, w.y, acc[p][1]);
-                            acc[p][2] = fmaf(av, w.z, acc[p][2]);
-                        }
+                        for (int p = 0; p < 2; ++p) fma4(acc[p], comp(a[p + kx], cc), w);
                     }
                 }
             }
@@ -257,7 +248,9 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
 #pragma unroll
             for (int co = 0; co < 3; ++co) {
                 float* dst = rgb + ((static_cast<long long>(n) * 3 + co) * OH + oy) * OW + ox;
-                const float v0 = fmaxf(acc[0][co] + sB3[co], 0.f), v1 = fmaxf(acc[1][co] + sB3[co], 0.f);
+                const float a0 = co == 0 ? acc[0][0].x : (co == 1 ? acc[0][0].y : acc[0][1].x);
+                const float a1 = co == 0 ? acc[1][0].x : (co == 1 ? acc[1][0].y : acc[1][1].x);
+                const float v0 = fmaxf(a0 + sB3[co], 0.f), v1 = fmaxf(a1 + sB3[co], 0.f);
                 if (ox + 1 < OW && ((reinterpret_cast<uintptr_t>(dst) & 7u) == 0)) {
                     *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
                 } else {

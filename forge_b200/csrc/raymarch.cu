@@ -153,9 +153,9 @@ raymarch_fwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
     const float4* qv = dens_quad + static_cast<long long>(v) * (D + 2) * Hq * Wq;
     const int row_y = Wp * 16, row_z = Hp * Wp * 16;   // float strides of the padded feature volume
 
-    float acc[8];
+    float2 acc[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int e = 0; e < 4; ++e) acc[e] = make_float2(0.f, 0.f);
     float T = 1.f, depth = 0.f;
     for (int k = kw0; k < kw1; ++k) {
         const float z = zs[k];
@@ -177,19 +177,22 @@ raymarch_fwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
         const float wk = sigma * T;
         if (wk != 0.f) {   // sigma != 0 implies act
             const float* p = fv + ((f.z0 + 1) * Hp + (f.y0 + 1)) * row_y + (f.x0 + 1) * 16;
-            float fs[8];
+            // packed FFMA2 (two fp32 FMAs per instruction on sm_100, per-component rounding = fmaf)
+            float2 fs[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) fs[e] = 0.f;
+            for (int e = 0; e < 4; ++e) fs[e] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int cn = 0; cn < 8; ++cn) {
                 const float wxy = (cn & 2) ? ((cn & 1) ? w11 : w01) : ((cn & 1) ? w10 : w00);
                 const float w = __fmul_rn(wxy, (cn & 4) ? f.wz1 : f.wz0);
                 const f8 val = ldg256(p + ((cn & 4) ? row_z : 0) + ((cn & 2) ? row_y : 0) + ((cn & 1) ? 16 : 0));
+                const float2 w2 = make_float2(w, w);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) fs[e] = fmaf(val.v[e], w, fs[e]);
+                for (int e = 0; e < 4; ++e) fs[e] = __ffma2_rn(make_float2(val.v[2 * e], val.v[2 * e + 1]), w2, fs[e]);
             }
+            const float2 wk2 = make_float2(wk, wk);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(wk, fs[e], acc[e]);
+            for (int e = 0; e < 4; ++e) acc[e] = __ffma2_rn(wk2, fs[e], acc[e]);
             depth = fmaf(wk, z, depth);
         }
         T = T * (1.f - sigma);
@@ -197,8 +200,8 @@ raymarch_fwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
     if (valid) {
         const long long pix = (static_cast<long long>(n) * Sh + i) * Sw + j;
         float4* o = reinterpret_cast<float4*>(out_feat + pix * 16 + c * 8);
-        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        o[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+        o[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
         if (c == 0) {
             out_sil[pix] = 1.f - T;
             if (out_depth) out_depth[pix] = depth;
