@@ -66,7 +66,11 @@ def main():
     K = sample['K_cv2'][0].to(DEV)
 
     def make_params():
-        q = torch.tensor([[1.0, 0.02, -0.01, 0.03]] * 4, device=DEV).requires_grad_(True)
+        # start near the ground-truth relative poses, like the reference does from the pose network's prediction
+        # (an identity rotation with the true translation points every camera away from the object: empty views,
+        # exactly-zero pose gradients and no raymarching work)
+        from forge_b200.models.model import _mat2quat
+        q = (_mat2quat(rel_gt)[:, :4] + torch.tensor([0.0, 0.02, -0.01, 0.03], device=DEV)).clone().requires_grad_(True)
         t = (rel_gt[:, :3, 3] + 0.01).clone().requires_grad_(True)
         return q, t
 
