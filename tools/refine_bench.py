@@ -109,10 +109,16 @@ def main():
         return F.mse_loss(rgb, target_rgb) + F.mse_loss(mask, target_mask)
 
     results = {}
+    from forge_b200.refine import prepare_for_pose_refinement
     arms = [("forge_b200", step_forge)] + ([] if args.no_ref else [("reference op sequence (oracle on GPU)", step_ref)])
     arms.append(("forge_b200, bf16 fusion+heads (channels-last weights)", step_forge))
+    arms.append(("forge_b200, prepare_for_pose_refinement (frozen weights, channels-last, fp32)", step_forge))
+    arms.append(("forge_b200, prepare_for_pose_refinement (frozen weights, bf16 fusion+heads, tensor-core decoder)", step_forge))
     for name, fn in arms:
-        if "bf16" in name:
+        if "prepare_for" in name:
+            bf = torch.bfloat16 if "bf16" in name else None
+            prepare_for_pose_refinement(model, fusion_dtype=bf, decoder_dtype=bf)
+        elif "bf16" in name:
             model.encoder_3d.channels_last_3d_()
             model.encoder_3d.compute_dtype = torch.bfloat16
         q, t = make_params()
