@@ -13,7 +13,7 @@ python tools/bench_kernels.py --reps 20 --ref --bwd > gpurun_out/${TAG}_kernels.
 python tools/bench_kernels.py --reps 10 --objects 1 --img 128 --vol 32 --pts 32 --ref --only k1,k2,relayout > gpurun_out/${TAG}_kernels_cfg1.jsonl 2>/dev/null; cat gpurun_out/${TAG}_kernels_cfg1.jsonl
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-clocks > gpurun_out/${TAG}_ncu_bench.log 2>&1
-for K in raymarch_fwd:k1 pack_volume:relayout decoder_fwd:volrender rotate_fwd:k2; do
+for K in raymarch_fwd:k1 pack_volume:relayout decoder_fwd:volrender decoder_tc:volrender rotate_fwd:k2; do
   PAT=${K%%:*}; ONLY=${K##*:}
   ncu --set full --clock-control none --import-source on -k regex:$PAT -s 2 -c 1 -f -o gpurun_out/${TAG}_$PAT \
       python tools/bench_kernels.py --reps 1 --only $ONLY > gpurun_out/${TAG}_ncu_$PAT.log 2>&1

@@ -46,6 +46,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--only", default="", help="run only the arms whose name contains this substring")
     args = ap.parse_args()
     torch.manual_seed(0)
     cfg = syn.make_config(img_size=256, n_pts_per_ray=64, use_gt_pose=True)
@@ -115,6 +116,8 @@ def main():
     arms.append(("forge_b200, prepare_for_pose_refinement (frozen weights, channels-last, fp32)", step_forge))
     arms.append(("forge_b200, prepare_for_pose_refinement (frozen weights, bf16 fusion+heads, tensor-core decoder)", step_forge))
     for name, fn in arms:
+        if args.only and args.only not in name:
+            continue
         if "prepare_for" in name:
             bf = torch.bfloat16 if "bf16" in name else None
             prepare_for_pose_refinement(model, fusion_dtype=bf, decoder_dtype=bf)
