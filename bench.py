@@ -290,14 +290,14 @@ def run_forge(args, rank, world, local_rank):
 
         # ---- secondary: the tensor-core (bf16, tcgen05) decoder on the raymarcher's output, same run --------------
         model.decoder_dtype = torch.bfloat16
-        wtc = model._decoder_pack(dev, tc=True)
+        wtc = model._decoder_pack(dev, kind='tc')
         rgb = torch.empty(N, 3, 2 * S, 2 * S, device=dev)
         dec_ms = []
         for it in range(3 + 10):
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            _lib.call("forge_decoder_tc_fwd", o_feat.data_ptr(), wtc.data_ptr(), rgb.data_ptr(), N, S, S, 0,
+            _lib.call("forge_decoder_tc_fwd", o_feat.data_ptr(), wtc.data_ptr(), rgb.data_ptr(), None, N, S, S, 0,
                       torch.cuda.current_stream(dev).cuda_stream)
             b.record()
             torch.cuda.synchronize(dev)

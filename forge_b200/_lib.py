@@ -26,9 +26,11 @@ _SIGNATURES = {
     "forge_rotate_fwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F] + [_I] * 5 + [_F]),
     "forge_rotate_bwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F, _F, _F] + [_I] * 5 + [_F]),
     "forge_decoder_wpack_floats": (_c.c_int, []),
-    "forge_decoder_fwd": (_c.c_int, [_F, _F, _F, _I, _I, _I, _F]),
+    "forge_decoder_fwd": (_c.c_int, [_F, _F, _F, _F, _I, _I, _I, _F]),
+    "forge_decoder_bwd_wpack_floats": (_c.c_int, []),
+    "forge_decoder_bwd_data": (_c.c_int, [_F, _F, _F, _F, _I, _I, _I, _F]),
     "forge_decoder_tc_wpack_bytes": (_c.c_int, []),
-    "forge_decoder_tc_fwd": (_c.c_int, [_F, _F, _F, _I, _I, _I, _I, _F]),
+    "forge_decoder_tc_fwd": (_c.c_int, [_F, _F, _F, _F, _I, _I, _I, _I, _F]),
     "forge_umma_probe": (_c.c_int, [_F, _I] + [_c.c_uint] * 6 + [_F, _F]),
     "forge_camera_prep_fwd": (_c.c_int, [_F, _F, _F, _I] + [_c.c_float] * 4 + [_F, _F, _F]),
     "forge_camera_prep_bwd": (_c.c_int, [_F, _F, _F, _I] + [_c.c_float] * 4 + [_F] * 5 + [_F]),
@@ -37,7 +39,7 @@ _SIGNATURES = {
     "forge_pose_affine_fwd": (_c.c_int, [_F, _I, _I, _F, _F, _F, _F]),
     "forge_sample_points": (_c.c_int, [_F, _I, _I, _I, _I, _I, _F, _F, _F]),
 }
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _lock = threading.Lock()
 _lib = None

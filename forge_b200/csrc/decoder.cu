@@ -71,8 +71,8 @@ __device__ __forceinline__ void fma4(float2 (&a)[2], float av, const float4& w) 
 __device__ __forceinline__ float get8(const float2 (&a)[4], int co) { return (co & 1) ? a[co >> 1].y : a[co >> 1].x; }
 
 __global__ void __launch_bounds__(kDecThreads, 1)
-decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack, float* __restrict__ rgb, int Sh, int Sw,
-                   int tiles_x) {
+decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack, float* __restrict__ rgb,
+                   unsigned* __restrict__ masks, int Sh, int Sw, int tiles_x) {
     extern __shared__ __align__(16) float sm[];
     float* sIn = sm;
     float* sL1 = sIn + SM_IN;
@@ -89,6 +89,9 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
     const int Y0 = tyi * TOY, X0 = txi * TOX;          // output-tile origin (even)
     const int OH = 2 * Sh, OW = 2 * Sw;
     const int tid = threadIdx.x;
+    // sign masks for the backward pass (decoder_bwd.cu): byte 0/1 = layer-1 channels 0-7 / 8-15, byte 2 = layer 2,
+    // byte 3 = rgb; every output pixel is written by the tile that owns it
+    unsigned char* mbytes = masks ? reinterpret_cast<unsigned char*>(masks + static_cast<long long>(n) * OH * OW) : nullptr;
 
     // ---- phase 0: weights by one bulk async copy (53 KB, no register staging) overlapped with the
     //      threads' own load of the input tile (zeros outside the image) ----
@@ -151,8 +154,15 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
             const int lc = 2 * (4 * g + p) + px, ox = X0 - 4 + lc;
             const bool inside = (oy >= 0 && oy < OH && ox >= 0 && ox < OW);     // conv zero padding of layer 2
             float v[8];
+            unsigned bits = 0;
 #pragma unroll
-            for (int co = 0; co < 8; ++co) v[co] = inside ? lrelu(get8(acc[p], co) + sB1[half * 8 + co]) : 0.f;
+            for (int co = 0; co < 8; ++co) {
+                const float pre = get8(acc[p], co) + sB1[half * 8 + co];
+                bits |= (pre > 0.f ? 1u : 0u) << co;
+                v[co] = inside ? lrelu(pre) : 0.f;
+            }
+            if (mbytes && inside && lr >= 4 && lr < 4 + TOY && lc >= 4 && lc < 4 + TOX)
+                mbytes[(static_cast<long long>(oy) * OW + ox) * 4 + half] = static_cast<unsigned char>(bits);
             float* dst = sL1 + lr * L1_RS + lc * L1_PS + half * 8;
             *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -210,8 +220,15 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
                 const float4 q0 = *reinterpret_cast<const float4*>(part + p * 8), q1 = *reinterpret_cast<const float4*>(part + p * 8 + 4);
                 const float o[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
                 float v[8];
+                unsigned bits = 0;
 #pragma unroll
-                for (int co = 0; co < 8; ++co) v[co] = inside ? lrelu(get8(acc[p], co) + o[co] + sB2[co]) : 0.f;
+                for (int co = 0; co < 8; ++co) {
+                    const float pre = get8(acc[p], co) + o[co] + sB2[co];
+                    bits |= (pre > 0.f ? 1u : 0u) << co;
+                    v[co] = inside ? lrelu(pre) : 0.f;
+                }
+                if (mbytes && inside && row >= 2 && row < 2 + TOY && lc >= 2 && lc < 2 + TOX)
+                    mbytes[(static_cast<long long>(oy) * OW + ox) * 4 + 2] = static_cast<unsigned char>(bits);
                 float* dst = sL2 + row * L2_RS + lc * L2_PS;
                 *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -244,6 +261,16 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
             }
         }
         const int oy = Y0 + row, ox = X0 + 2 * grp;
+        if (oy < OH && mbytes) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                if (ox + p < OW) {
+                    const unsigned bits = (acc[p][0].x + sB3[0] > 0.f ? 1u : 0u) | (acc[p][0].y + sB3[1] > 0.f ? 2u : 0u) |
+                                          (acc[p][1].x + sB3[2] > 0.f ? 4u : 0u);
+                    mbytes[(static_cast<long long>(oy) * OW + ox + p) * 4 + 3] = static_cast<unsigned char>(bits);
+                }
+            }
+        }
         if (oy < OH) {
 #pragma unroll
             for (int co = 0; co < 3; ++co) {
@@ -266,8 +293,8 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wpack,
 
 extern "C" int forge_decoder_wpack_floats(void) { return forge::WPACK_N; }
 
-extern "C" int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float* rgb_nchw, int N, int S_h, int S_w,
-                                 void* stream) {
+extern "C" int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float* rgb_nchw, unsigned* sign_masks, int N,
+                                 int S_h, int S_w, void* stream) {
     using namespace forge;
     const char* fn = "forge_decoder_fwd";
     if (!x_nhwc || !wpack || !rgb_nchw) return fail(fn, "null pointer");
@@ -284,7 +311,7 @@ extern "C" int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float*
     }
     const int tiles_x = (2 * S_w + TOX - 1) / TOX, tiles_y = (2 * S_h + TOY - 1) / TOY;
     dim3 grid(tiles_x * tiles_y, N);
-    decoder_fwd_kernel<<<grid, kDecThreads, smem, static_cast<cudaStream_t>(stream)>>>(x_nhwc, wpack, rgb_nchw, S_h, S_w,
-                                                                                       tiles_x);
+    decoder_fwd_kernel<<<grid, kDecThreads, smem, static_cast<cudaStream_t>(stream)>>>(x_nhwc, wpack, rgb_nchw, sign_masks,
+                                                                                       S_h, S_w, tiles_x);
     return check_launch(fn);
 }

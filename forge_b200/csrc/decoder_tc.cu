@@ -173,8 +173,8 @@ __device__ __forceinline__ uint32_t act_pack(float a0, float a1, float b0, float
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__ wpack, float* __restrict__ rgb, int Sh,
-                  int Sw, int tiles_x, int tiles_y, int total_tiles) {
+decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__ wpack, float* __restrict__ rgb,
+                  unsigned* __restrict__ masks, int Sh, int Sw, int tiles_x, int tiles_y, int total_tiles) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* sW = smem + SM_W;
     unsigned char* sIn = smem + SM_IN;
@@ -304,6 +304,16 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
                         unsigned char* dst = sL1 + (((lc & 7) * 2) * L1_PLANE + lr * GP + (lc >> 3)) * 16;
                         *reinterpret_cast<uint4*>(dst) = q0;
                         *reinterpret_cast<uint4*>(dst + L1_PLANE * 16) = q1;
+                        if (masks && lr >= 4 && lr < 4 + TOY && lc >= 4 && lc < 4 + TOX && oy < OH && ox < OW) {
+                            // sign bits of the 16 pre-activations for the backward pass (decoder_bwd.cu), low half-word
+                            const float bb[16] = {b1a.x, b1a.y, b1a.z, b1a.w, b1b.x, b1b.y, b1b.z, b1b.w,
+                                                  b1c.x, b1c.y, b1c.z, b1c.w, b1d.x, b1d.y, b1d.z, b1d.w};
+                            unsigned bits = 0;
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) bits |= (a[c] + bb[c] > 0.f ? 1u : 0u) << c;
+                            reinterpret_cast<unsigned short*>(masks + (static_cast<long long>(n) * OH + oy) * OW + ox)[0] =
+                                static_cast<unsigned short>(bits);
+                        }
                     }
                 }
             }
@@ -343,6 +353,15 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
                     q = make_uint4(act_pack(a[0], a[1], b2a.x, b2a.y), act_pack(a[2], a[3], b2a.z, b2a.w),
                                    act_pack(a[4], a[5], b2b.x, b2b.y), act_pack(a[6], a[7], b2b.z, b2b.w));
                 *reinterpret_cast<uint4*>(sL2 + (delta * L2_PLANE + row) * 16) = q;
+                const int xl = 8 * xg + delta;
+                if (masks && yr >= 2 && yr < 2 + TOY && xl >= 2 && xl < 2 + TOX && oy < OH && ox < OW) {
+                    const float bb[8] = {b2a.x, b2a.y, b2a.z, b2a.w, b2b.x, b2b.y, b2b.z, b2b.w};
+                    unsigned bits = 0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) bits |= (a[c] + bb[c] > 0.f ? 1u : 0u) << c;
+                    reinterpret_cast<unsigned char*>(masks + (static_cast<long long>(n) * OH + oy) * OW + ox)[2] =
+                        static_cast<unsigned char>(bits);
+                }
             }
         }
         proxy_fence();
@@ -373,6 +392,17 @@ decoder_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__
             const int oy = Y0 + yr, ox = X0 + 8 * xg + 4 * grp;
             if (yr < TOY && xg < TOX / 8 && oy < OH && ox < OW) {
                 const float bias[3] = {b3.x, b3.y, b3.z};
+                if (masks) {
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        if (ox + d < OW) {
+                            const unsigned bits = (acc[8 * d] + b3.x > 0.f ? 1u : 0u) | (acc[8 * d + 1] + b3.y > 0.f ? 2u : 0u) |
+                                                  (acc[8 * d + 2] + b3.z > 0.f ? 4u : 0u);
+                            reinterpret_cast<unsigned char*>(masks + (static_cast<long long>(n) * OH + oy) * OW + ox + d)[3] =
+                                static_cast<unsigned char>(bits);
+                        }
+                    }
+                }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float b = bias[c];
@@ -447,8 +477,8 @@ umma_probe_kernel(const unsigned char* __restrict__ image, int image_bytes, unsi
 
 extern "C" int forge_decoder_tc_wpack_bytes(void) { return forge::dtc::WPACK_BYTES; }
 
-extern "C" int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, float* rgb_nchw, int N, int S_h, int S_w,
-                                    int max_ctas, void* stream) {
+extern "C" int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, float* rgb_nchw, unsigned* sign_masks, int N,
+                                    int S_h, int S_w, int max_ctas, void* stream) {
     using namespace forge;
     using namespace forge::dtc;
     const char* fn = "forge_decoder_tc_fwd";
@@ -474,7 +504,8 @@ extern "C" int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, floa
     if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
     if (total < ctas) ctas = static_cast<int>(total);
     decoder_tc_kernel<<<ctas, kThreads, SM_TOTAL, static_cast<cudaStream_t>(stream)>>>(
-        x_nhwc, static_cast<const unsigned char*>(wpack), rgb_nchw, S_h, S_w, tiles_x, tiles_y, static_cast<int>(total));
+        x_nhwc, static_cast<const unsigned char*>(wpack), rgb_nchw, sign_masks, S_h, S_w, tiles_x, tiles_y,
+        static_cast<int>(total));
     return check_launch(fn);
 }
 

@@ -166,15 +166,18 @@ class VolRender(nn.Module):
             else:
                 return rendered_imgs, rendered_silhouettes
 
-    def _decoder_pack(self, device, tc=False):
-        """Weight pack for the fused decoder (fp32, BN folded) or the tensor-core decoder (bf16 B tiles),
-        rebuilt only when a parameter / buffer changed."""
+    def _decoder_pack(self, device, kind='fp32'):
+        """Weight pack for the fused fp32 decoder (BN folded), the tensor-core decoder ('tc': bf16 B tiles) or the
+        constant-weights backward kernel ('bwd'); rebuilt only when a parameter / buffer changed."""
         tensors = list(self.conv_rgb.parameters()) + list(self.conv_rgb.buffers())
-        key = (str(device), tc) + tuple((t.data_ptr(), t._version) for t in tensors)
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in tensors)
         if self._wpack is None or self._wpack[0] != key:
-            pack = ops.pack_decoder_tc_weights if tc else ops.pack_decoder_weights
-            self._wpack = (key, pack(self.conv_rgb))
-        return self._wpack[1]
+            self._wpack = (key, {})
+        packs = self._wpack[1]
+        if kind not in packs:
+            fn = {'fp32': ops.pack_decoder_weights, 'tc': ops.pack_decoder_tc_weights, 'bwd': ops.pack_decoder_bwd_weights}[kind]
+            packs[kind] = fn(self.conv_rgb)
+        return packs[kind]
 
     def decode(self, feat_nhwc):
         """[N,S,S,16] composited features -> relu(conv_rgb(.)) [N,3,2S,2S] (reference :73).
@@ -182,10 +185,16 @@ class VolRender(nn.Module):
         tcgen05 tensor cores (decoder_dtype torch.bfloat16); training mode (batch-statistics BN) or a
         non-default decoder: the module's own cuDNN convs on the NHWC buffer."""
         fused = self.fused_decoder and not self.training and self.k_size == 5 and feat_nhwc.is_cuda
-        if fused and self.decoder_dtype is None:
-            return ops.decoder_fused(feat_nhwc, self._decoder_pack(feat_nhwc.device), self.conv_rgb)
-        if fused and self.decoder_dtype == torch.bfloat16:        # tcgen05 implicit GEMMs (decoder_tc.cu)
-            return ops.decoder_tc(feat_nhwc, self._decoder_pack(feat_nhwc.device, tc=True), self.conv_rgb)
+        if fused and self.decoder_dtype in (None, torch.bfloat16):
+            dev = feat_nhwc.device
+            # constant decoder weights + a gradient wanted for the features (pose refinement): the backward pass is
+            # one kernel (forge_decoder_bwd_data) and needs its own weight pack
+            bwd = None
+            if feat_nhwc.requires_grad and torch.is_grad_enabled() and not any(p.requires_grad for p in self.conv_rgb.parameters()):
+                bwd = self._decoder_pack(dev, kind='bwd')
+            if self.decoder_dtype is None:
+                return ops.decoder_fused(feat_nhwc, self._decoder_pack(dev), self.conv_rgb, bwd_pack=bwd)
+            return ops.decoder_tc(feat_nhwc, self._decoder_pack(dev, kind='tc'), self.conv_rgb, bwd_pack=bwd)   # tcgen05
         x = feat_nhwc.permute(0, 3, 1, 2)                             # NCHW view of the NHWC kernel output
         if self.decoder_dtype is None:
             return F.relu(self.conv_rgb(x))

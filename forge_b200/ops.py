@@ -242,40 +242,78 @@ def pack_decoder_weights(conv_rgb):
     return pack
 
 
+def pack_decoder_bwd_weights(conv_rgb):
+    """fp32 weight pack of forge_decoder_bwd_data (flipped / transposed filters, BN scales folded; forge_b200.h)."""
+    ct, bn1, _, c2, bn2, _, c3 = conv_rgb
+    with torch.no_grad():
+        s1 = bn1.weight / torch.sqrt(bn1.running_var + bn1.eps)
+        s2 = bn2.weight / torch.sqrt(bn2.running_var + bn2.eps)
+        w3b = c3.weight.flip(2, 3).permute(2, 3, 0, 1)                               # [ky, kx, co 3, c 8]
+        w2b = (c2.weight * s2.view(8, 1, 1, 1)).flip(2, 3).permute(2, 3, 0, 1)       # [ky, kx, co 8, ci 16]
+        wd = (ct.weight * s1.view(1, 16, 1, 1)).permute(2, 3, 1, 0)                  # [u, v, co 16, ci 16]
+        pack = torch.cat([t.reshape(-1).float() for t in (w3b, w2b, wd)]).contiguous()
+    assert pack.numel() == _lib.load().forge_decoder_bwd_wpack_floats()
+    return pack
+
+
+def _decoder_backward(ctx, g):
+    """Shared backward of the fused decoders.  Constant decoder weights (pose refinement): one kernel from the sign
+    masks the forward pass saved.  Trainable weights: re-run the module's own convs under autograd (cuDNN)."""
+    x_nhwc, masks = ctx.saved_tensors
+    params = [p for p in ctx.conv_rgb.parameters() if p.requires_grad]
+    if not params and masks.numel():
+        N, Sh, Sw, _ = x_nhwc.shape
+        g = _f32c(g)
+        gx = torch.empty_like(x_nhwc)
+        wb = pack_decoder_bwd_weights(ctx.conv_rgb) if ctx.bwd_pack is None else ctx.bwd_pack
+        with torch.cuda.device(g.device):
+            _lib.call("forge_decoder_bwd_data", _ptr(g), _ptr(masks), _ptr(wb), _ptr(gx), N, Sh, Sw, _stream(g))
+        return gx
+    with torch.enable_grad():
+        xi = x_nhwc.detach().requires_grad_(True)
+        y = torch.relu(ctx.conv_rgb(xi.permute(0, 3, 1, 2)))
+        grads = torch.autograd.grad(y, [xi] + params, g, allow_unused=True)
+    for p, gp in zip(params, grads[1:]):        # weights are not Function inputs: accumulate like autograd would
+        if gp is not None:
+            gp = gp.contiguous()
+            p.grad = gp if p.grad is None else p.grad + gp
+    return grads[0]
+
+
+def _decoder_masks(ctx, x_nhwc, conv_rgb):
+    """uint32 sign-mask buffer when the input needs a gradient and the decoder weights are constants, else empty."""
+    N, Sh, Sw, _ = x_nhwc.shape
+    want = ctx.needs_input_grad[0] and not any(p.requires_grad for p in conv_rgb.parameters())
+    return torch.empty((N, 2 * Sh, 2 * Sw) if want else (0,), dtype=torch.int32, device=x_nhwc.device)
+
+
 class _Decoder(torch.autograd.Function):
-    """Fused inference decoder; the backward pass re-runs the module's own convs under autograd (cuDNN)."""
+    """Fused fp32 inference decoder (see _decoder_backward for the backward pass)."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, wpack, conv_rgb):
+    def forward(ctx, x_nhwc, wpack, conv_rgb, bwd_pack):
         N, Sh, Sw, _ = x_nhwc.shape
         rgb = torch.empty(N, 3, 2 * Sh, 2 * Sw, dtype=torch.float32, device=x_nhwc.device)
+        masks = _decoder_masks(ctx, x_nhwc, conv_rgb)
         with torch.cuda.device(x_nhwc.device):
-            _lib.call("forge_decoder_fwd", _ptr(x_nhwc), _ptr(wpack), _ptr(rgb), N, Sh, Sw, _stream(x_nhwc))
-        ctx.conv_rgb = conv_rgb
-        ctx.save_for_backward(x_nhwc)
+            _lib.call("forge_decoder_fwd", _ptr(x_nhwc), _ptr(wpack), _ptr(rgb), _ptr(masks) if masks.numel() else None,
+                      N, Sh, Sw, _stream(x_nhwc))
+        ctx.conv_rgb, ctx.bwd_pack = conv_rgb, bwd_pack
+        ctx.save_for_backward(x_nhwc, masks)
         return rgb
 
     @staticmethod
     def backward(ctx, g):
-        (x_nhwc,) = ctx.saved_tensors
-        with torch.enable_grad():
-            xi = x_nhwc.detach().requires_grad_(True)
-            y = torch.relu(ctx.conv_rgb(xi.permute(0, 3, 1, 2)))
-            params = [p for p in ctx.conv_rgb.parameters() if p.requires_grad]
-            grads = torch.autograd.grad(y, [xi] + params, g, allow_unused=True)
-        for p, gp in zip(params, grads[1:]):        # weights are not Function inputs: accumulate like autograd would
-            if gp is not None:
-                gp = gp.contiguous()
-                p.grad = gp if p.grad is None else p.grad + gp
-        return grads[0], None, None
+        return _decoder_backward(ctx, g), None, None, None
 
 
-def decoder_fused(x_nhwc, wpack, conv_rgb):
-    """x [N,S,S,16] NHWC -> relu(conv_rgb(x)) [N,3,2S,2S] through the fused kernel (eval-mode BN)."""
+def decoder_fused(x_nhwc, wpack, conv_rgb, bwd_pack=None):
+    """x [N,S,S,16] NHWC -> relu(conv_rgb(x)) [N,3,2S,2S] through the fused kernel (eval-mode BN).  bwd_pack:
+    optional cached pack_decoder_bwd_weights(conv_rgb) for the constant-weights backward."""
     _require_cuda(x_nhwc, wpack)
     if x_nhwc.shape[-1] != 16:
         raise ValueError("the decoder input must have 16 channels")
-    return _Decoder.apply(_f32c(x_nhwc), wpack, conv_rgb)
+    return _Decoder.apply(_f32c(x_nhwc), wpack, conv_rgb, bwd_pack)
 
 
 # ---- tensor-core (bf16) decoder ------------------------------------------------------------------
@@ -333,31 +371,32 @@ def pack_decoder_tc_weights(conv_rgb):
 
 
 class _DecoderTC(torch.autograd.Function):
-    """bf16 tensor-core inference decoder; the backward pass re-runs the module's own convs (cuDNN)."""
+    """bf16 tensor-core inference decoder (see _decoder_backward for the backward pass)."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, wpack, conv_rgb, max_ctas):
+    def forward(ctx, x_nhwc, wpack, conv_rgb, max_ctas, bwd_pack):
         N, Sh, Sw, _ = x_nhwc.shape
         rgb = torch.empty(N, 3, 2 * Sh, 2 * Sw, dtype=torch.float32, device=x_nhwc.device)
+        masks = _decoder_masks(ctx, x_nhwc, conv_rgb)
         with torch.cuda.device(x_nhwc.device):
-            _lib.call("forge_decoder_tc_fwd", _ptr(x_nhwc), _ptr(wpack), _ptr(rgb), N, Sh, Sw, int(max_ctas),
-                      _stream(x_nhwc))
-        ctx.conv_rgb = conv_rgb
-        ctx.save_for_backward(x_nhwc)
+            _lib.call("forge_decoder_tc_fwd", _ptr(x_nhwc), _ptr(wpack), _ptr(rgb), _ptr(masks) if masks.numel() else None,
+                      N, Sh, Sw, int(max_ctas), _stream(x_nhwc))
+        ctx.conv_rgb, ctx.bwd_pack = conv_rgb, bwd_pack
+        ctx.save_for_backward(x_nhwc, masks)
         return rgb
 
     @staticmethod
     def backward(ctx, g):
-        return _Decoder.backward(ctx, g) + (None,)
+        return _decoder_backward(ctx, g), None, None, None, None
 
 
-def decoder_tc(x_nhwc, wpack, conv_rgb, max_ctas=0):
+def decoder_tc(x_nhwc, wpack, conv_rgb, max_ctas=0, bwd_pack=None):
     """x [N,S,S,16] NHWC fp32 -> relu(conv_rgb(x)) [N,3,2S,2S] fp32 on the tcgen05 tensor cores (bf16 operands,
     fp32 accumulation, eval-mode BN)."""
     _require_cuda(x_nhwc, wpack)
     if x_nhwc.shape[-1] != 16:
         raise ValueError("the decoder input must have 16 channels")
-    return _DecoderTC.apply(_f32c(x_nhwc), wpack, conv_rgb, max_ctas)
+    return _DecoderTC.apply(_f32c(x_nhwc), wpack, conv_rgb, max_ctas, bwd_pack)
 
 
 def umma_probe(image_u8, a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 10
+#define FORGE_ABI_VERSION 11
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -92,8 +92,23 @@ long long forge_raymarch_bwd_workspace(int N, int S_h, int S_w, int P);
  *     W3[ky][kx][ci][4]          = W3[co][ci][ky][kx], co = 3 zero          (25*8*4)
  *     b1[16] = (bt - mean1) s1 + beta1,  b2[8] likewise,  b3[4]             s = gamma / sqrt(var + eps) */
 int forge_decoder_wpack_floats(void);
-int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float* rgb_nchw, int N, int S_h, int S_w,
-                      void* stream);
+int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float* rgb_nchw, unsigned* sign_masks, int N, int S_h,
+                      int S_w, void* stream);
+
+/* Both forward decoders optionally (sign_masks != NULL) emit one uint32 per output pixel [N][2 S_h][2 S_w] with the
+ * signs of the three pre-activations (bits 0-15 layer 1, 16-23 layer 2, 24-26 rgb; 1 = positive): all the backward
+ * pass needs from the forward one, since the decoder is piece-wise linear.
+ *
+ * forge_decoder_bwd_data: g_x = (d relu(conv_rgb(x)) / d x)^T g_rgb in one fp32 kernel -- the pose-only backward of
+ * models/volume_render.py:73 when the decoder weights are constants (test-time pose optimisation,
+ * kubric_eval.py:450-504).  g_rgb [N][3][2S][2S], masks from the forward call, g_x [N][S][S][16] (written).
+ *   wpack_bwd (forge_decoder_bwd_wpack_floats() floats, 16-byte aligned), BN scales folded like the forward pack:
+ *     W3b[ky][kx][co < 3][c < 8]    = W3[co][c][4-ky][4-kx]
+ *     W2b[ky][kx][co < 8][ci < 16]  = W2[co][ci][4-ky][4-kx] * s2[co]
+ *     Wd[u][v][co < 16][ci < 16]    = Wt[ci][co][u][v] * s1[co] */
+int forge_decoder_bwd_wpack_floats(void);
+int forge_decoder_bwd_data(const float* g_rgb_nchw, const unsigned* sign_masks, const float* wpack_bwd, float* g_x_nhwc,
+                           int N, int S_h, int S_w, void* stream);
 
 /* ---- tensor-core decoder (bf16 operands, fp32 accumulate; tcgen05.mma + TMEM) ---------------
  * Same function as forge_decoder_fwd -- relu(conv_rgb(x)), models/volume_render.py:29-37,73, eval-mode
@@ -113,8 +128,8 @@ int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float* rgb_nchw, 
  *     b1 = (bias_t - mean1) s1 + beta1, b2 likewise, b3 = the last conv's bias.
  *   max_ctas: 0 = two persistent CTAs per SM, otherwise an upper bound on the grid. */
 int forge_decoder_tc_wpack_bytes(void);
-int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, float* rgb_nchw, int N, int S_h, int S_w,
-                         int max_ctas, void* stream);
+int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, float* rgb_nchw, unsigned* sign_masks, int N, int S_h,
+                         int S_w, int max_ctas, void* stream);
 
 /* Test hook: ONE tcgen05.mma (M=128, N=16, K=16, bf16 x bf16 -> fp32, both operands K-major without
  * swizzle) over a caller-built shared-memory image; pins the descriptor semantics the decoder relies on:

@@ -125,3 +125,47 @@ def test_decoder_tc_small_grid_and_module_switch():
     xg = x.clone().requires_grad_(True)
     m.decode(xg).sum().backward()
     assert torch.isfinite(xg.grad).all() and xg.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("N,S,tc", [(2, 16, False), (1, 21, False), (3, 64, False), (5, 128, False), (2, 24, True), (1, 13, True)])
+def test_decoder_constant_weights_backward_kernel_matches_autograd(N, S, tc):
+    """forge_decoder_bwd_data (sign masks from the forward kernel) == autograd through the module's convs when the
+    decoder weights are constants; fp32 forward: <= 1e-5 of the gradient scale (same piece-wise linear map, fp32
+    accumulation order differs); bf16 tensor-core forward: the kernel differentiates the map the forward kernel
+    evaluated (its own sign pattern), checked against the fp32 module's gradient at bf16-level tolerance."""
+    torch.manual_seed(N * 10 + S)
+    m = VolRender(syn.make_config(img_size=2 * S, n_pts_per_ray=8)).to(DEV)
+    _randomise_bn(m)
+    m.eval()
+    for p in m.parameters():
+        p.requires_grad_(False)
+    if tc:
+        m.decoder_dtype = torch.bfloat16
+    x = torch.randn(N, S, S, 16, device=DEV)
+    g = torch.randn(N, 3, 2 * S, 2 * S, device=DEV)
+    xk = x.clone().requires_grad_(True)
+    out = m.decode(xk)
+    out.backward(g)
+    xr = x.clone().requires_grad_(True)
+    ref = F.relu(m.conv_rgb(xr.permute(0, 3, 1, 2)))
+    ref.backward(g)
+    scale = xr.grad.abs().max().item()
+    err = (xk.grad - xr.grad).abs()
+    print("decoder bwd N=%d S=%d tc=%s: max err %.2e mean %.2e (grad max %.2e)" % (N, S, tc, err.max().item(), err.mean().item(), scale))
+    if tc:
+        assert err.mean().item() <= 2e-2 * scale       # a few sign flips near zero pre-activations differ from the fp32 map
+    else:
+        assert err.max().item() <= 1e-5 * max(1.0, scale) + 1e-4 * scale
+
+
+def test_decoder_backward_falls_back_to_module_convs_for_trainable_weights():
+    torch.manual_seed(1)
+    m = VolRender(syn.make_config(img_size=64, n_pts_per_ray=8)).to(DEV).eval()
+    x = torch.randn(2, 32, 32, 16, device=DEV)
+    xk = x.clone().requires_grad_(True)
+    m.decode(xk).sum().backward()
+    assert m.conv_rgb[0].weight.grad is not None and xk.grad is not None
+    xr = x.clone().requires_grad_(True)
+    m.zero_grad()
+    F.relu(m.conv_rgb(xr.permute(0, 3, 1, 2))).sum().backward()
+    assert torch.allclose(xk.grad, xr.grad, atol=1e-4, rtol=1e-4)
