@@ -119,6 +119,32 @@ def main():
             report("decoder TENSOR-CORE bf16 kernel (forge_decoder_tc_fwd, tcgen05)", ms, best, (x.numel() + N * 3 * img * img) * 4,
                    bf16_TFLOPs_useful=round(N * (2 * S) ** 2 * 6104 * 2 / ms / 1e9, 2))
             m.decoder_dtype = None
+            # constant-weights backward (pose refinement): one kernel from the forward's sign masks vs cuDNN through autograd
+            masks = torch.empty(N, img, img, dtype=torch.int32, device=DEV)
+            rgb_tmp = torch.empty(N, 3, img, img, device=DEV)
+            _lib.call("forge_decoder_fwd", x.data_ptr(), m._decoder_pack(DEV).data_ptr(), rgb_tmp.data_ptr(), masks.data_ptr(),
+                      N, S, S, torch.cuda.current_stream().cuda_stream)
+            wb = m._decoder_pack(DEV, kind='bwd')
+            g_rgb = torch.randn(N, 3, img, img, device=DEV)
+            gx = torch.empty_like(x)
+            ms, best = timeit(lambda: _lib.call("forge_decoder_bwd_data", g_rgb.data_ptr(), masks.data_ptr(), wb.data_ptr(),
+                                                gx.data_ptr(), N, S, S, torch.cuda.current_stream().cuda_stream), args.reps, flush)
+            report("decoder BACKWARD-DATA kernel, constant weights (forge_decoder_bwd_data)", ms, best, None,
+                   fp32_TFLOPs=round(N * (2 * S) ** 2 * 7930 * 2 / ms / 1e9, 2))
+            ms, best = timeit(lambda: _lib.call("forge_decoder_fwd", x.data_ptr(), m._decoder_pack(DEV).data_ptr(), rgb_tmp.data_ptr(),
+                                                masks.data_ptr(), N, S, S, torch.cuda.current_stream().cuda_stream), args.reps, flush)
+            report("decoder FUSED fp32 kernel + sign-mask emission", ms, best, None)
+            for p_ in m.conv_rgb.parameters():
+                p_.requires_grad_(False)
+
+            def cudnn_bwd():
+                with torch.enable_grad():
+                    xi = x.detach().requires_grad_(True)
+                    torch.relu(m.conv_rgb(xi.permute(0, 3, 1, 2))).backward(g_rgb)
+                return xi.grad
+            ms, best = timeit(cudnn_bwd, max(3, args.reps // 2), flush)
+            report("decoder conv_rgb forward + backward-data through autograd (cuDNN, constant weights)", ms, best, None)
+            del masks, rgb_tmp, g_rgb, gx
             m.fused_decoder = False
             for name, setup in (("fp32 (TF32 allowed, torch default)", lambda: None),
                                 ("fp32 strict (allow_tf32=False)", lambda: setattr(torch.backends.cudnn, 'allow_tf32', False)),
