@@ -423,3 +423,25 @@ def test_rotate_non_cubic_volume():
     grid = torch.einsum('mab,dhwb->mdhwa', A[:, :3, :], Pm) / gmax
     ref = torch.nn.functional.grid_sample(vox[0, 1:], grid, mode='bilinear', padding_mode='zeros', align_corners=False)
     assert (out[0, 1:].cpu() - ref).abs().max().item() <= TOL
+
+
+@pytest.mark.parametrize("dtype", [None, torch.bfloat16])
+def test_volrender_forward_replays_from_a_cuda_graph(dtype):
+    """Every C-ABI entry point is capture-safe: the whole VolRender.forward (camera prep, pack, raymarch, decoder,
+    upsample) captured in one CUDA graph returns the eager result bit for bit, also for new inputs."""
+    from forge_b200.pipeline import GraphedVolRender
+    img, vol, P, b, t = 64, 32, 32, 1, 5
+    m = VolRender(syn.make_config(img_size=img, n_pts_per_ray=P)).to(DEV).eval()
+    m.decoder_dtype = dtype
+    g = GraphedVolRender(m, b * t, b, vol, render_depth=True, return_origin_proj=True)
+    for seed in (0, 1):
+        inp = syn.render_inputs(b, t, img, vol, seed=seed, device=DEV)
+        with torch.no_grad():
+            eager = m(dict(R=inp['R'], T=inp['T'], K=inp['K'].clone()), inp['feat'], inp['dens'], render_depth=True,
+                      return_origin_proj=True, view2vol=inp['view2vol'])
+        K = inp['K'].clone()
+        out = g(dict(R=inp['R'], T=inp['T'], K=K), inp['feat'], inp['dens'], inp['view2vol'])
+        assert torch.equal(K, inp['K'] / 2.0 * torch.tensor([[1., 1, 1], [1, 1, 1], [0, 0, 0]], device=DEV)
+                           + torch.tensor([[0., 0, 0], [0, 0, 0], [0, 0, 1]], device=DEV))   # halved in place, K[2,2] = 1
+        for a, e in zip(out, eager):
+            assert torch.equal(a, e)
