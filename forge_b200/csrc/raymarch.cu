@@ -117,25 +117,38 @@ __device__ __forceinline__ f8 ldg256(const float* p) {
     return r;
 }
 
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kRmThreads, kMinBlocks)
+// i-th element of the sequence c, c+1, c-1, c+2, c-2, ... over [0, n) with c the (lower) middle
+__device__ __forceinline__ int centre_out(int i, int n) {
+    const int c = (n - 1) >> 1;
+    return (i & 1) ? c + ((i + 1) >> 1) : c - (i >> 1);
+}
+
+// CTA = kWX x kWY warps, each marching a 4x4 pixel patch: (4 kWX) x (4 kWY) pixel tile
+template <int kMinBlocks, int kWX, int kWY>
+__global__ void __launch_bounds__(32 * kWX * kWY, kMinBlocks)
 raymarch_fwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict__ dens_quad,
                     const int* __restrict__ view2vol, const float* __restrict__ cam12, const float* __restrict__ zs_g,
                     float* __restrict__ out_feat, float* __restrict__ out_sil, float* __restrict__ out_depth, int D,
                     int H, int W, int Sh, int Sw, int P, int tiles_x) {
     __shared__ float zs[kMaxP];
     __shared__ float cam[12];
-    const int n = blockIdx.y;
-    for (int k = threadIdx.x; k < P; k += kRmThreads) zs[k] = zs_g[k];
+    // Heavy-first schedule: CTAs are dispatched in (blockIdx.x, then blockIdx.y) order; map that order to
+    // (tile rank, view) with the views interleaved and the tiles ranked centre-out, so the long CTAs (rays through the
+    // middle of the volume) start first and the last wave consists of the short border tiles (ncu: SMs were idle
+    // 9 % of the launch with the row-major order).
+    const int order = blockIdx.y * gridDim.x + blockIdx.x, n_views = gridDim.y, tiles_y = gridDim.x / tiles_x;
+    const int rank = order / n_views, n = order - rank * n_views;
+    const int ri = rank / tiles_x, ci = rank - ri * tiles_x;
+    const int ty = centre_out(ri, tiles_y), tx = centre_out(ci, tiles_x);
+    for (int k = threadIdx.x; k < P; k += 32 * kWX * kWY) zs[k] = zs_g[k];
     if (threadIdx.x < 12) cam[threadIdx.x] = cam12[n * 12 + threadIdx.x];
     __syncthreads();
 
-    // 16x8 pixel tile per CTA, 4x4 patch per warp, 2 lanes per ray
+    // 4x4 patch per warp, 2 lanes per ray
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = lane & 1, q = lane >> 1;
-    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-    const int j = tx * 16 + (warp & 3) * 4 + (q & 3);
-    const int i = ty * 8 + (warp >> 2) * 4 + (q >> 2);
+    const int j = tx * (4 * kWX) + (warp % kWX) * 4 + (q & 3);
+    const int i = ty * (4 * kWY) + (warp / kWX) * 4 + (q >> 2);
     const bool valid = (i < Sh) && (j < Sw);
     Ray r = make_ray(cam, i, j, zs, P, D, H, W);
     if (!valid) r.k1 = 0;
@@ -237,7 +250,10 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
     // per-CTA stash [P][3][128 rays] in the caller's workspace (L2-resident between the two passes);
     // keeping it out of shared memory leaves the whole unified L1 to the corner gathers
     float* stash = workspace + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * P * 3 * kRaysPerCta;
-    const int n = blockIdx.y;
+    // heavy-first schedule, as in the forward kernel: views interleaved, tiles ranked centre-out
+    const int order = blockIdx.y * gridDim.x + blockIdx.x, n_views = gridDim.y, tiles_y = gridDim.x / tiles_x;
+    const int rank = order / n_views, n = order - rank * n_views;
+    const int ty = centre_out(rank / tiles_x, tiles_y), tx = centre_out(rank % tiles_x, tiles_x);
 
     for (int k = threadIdx.x; k < P; k += kRmThreads) zs[k] = zs_g[k];
     if (threadIdx.x < 12) cam[threadIdx.x] = cam12[n * 12 + threadIdx.x];
@@ -246,7 +262,6 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
     const bool need_feat = grad_feat_pad != nullptr, need_dens = grad_dens_pad != nullptr, need_cam = grad_cam != nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = lane & 1, q = lane >> 1, ray = threadIdx.x >> 1;
-    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int j = tx * 16 + (warp & 3) * 4 + (q & 3);
     const int i = ty * 8 + (warp >> 2) * 4 + (q >> 2);
     const bool valid = (i < Sh) && (j < Sw);
@@ -442,23 +457,39 @@ extern "C" int forge_raymarch_fwd(const float* feat_pad, const float* dens_quad,
     if (P > kMaxP) return fail(fn, "n_pts_per_ray exceeds 512");
     if ((reinterpret_cast<uintptr_t>(feat_pad) & 31u) || !aligned16(dens_quad) || !aligned16(out_feat))
         return fail(fn, "feat_pad must be 32-byte aligned, dens_quad / out_feat 16-byte aligned");
-    const int tiles_x = (S_w + 15) / 16, tiles_y = (S_h + 7) / 8;
-    dim3 grid(tiles_x * tiles_y, N);
     static const int min_blocks = [] {          // tuning knob (development): resident CTAs per SM the kernel is built for
         const char* e = getenv("FORGE_K1_MINBLOCKS");
         return e ? atoi(e) : 3;         // measured on B200, cfg-2: 2 -> 0.411 ms, 3 -> 0.395 ms, 4 -> 0.394 ms
     }();
+    static const int shape = [] {               // tuning knob (development): CTA shape in warps, "XY" (41 = 4 x 1 warps)
+        const char* e = getenv("FORGE_K1_SHAPE");
+        return e ? atoi(e) : 41;
+    }();
+    const int wx = shape / 10, wy = shape % 10;
+    const int tiles_x = (S_w + 4 * wx - 1) / (4 * wx), tiles_y = (S_h + 4 * wy - 1) / (4 * wy);
+    dim3 grid(tiles_x * tiles_y, N);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float4* dq = reinterpret_cast<const float4*>(dens_quad);
-    if (min_blocks == 3)
-        raymarch_fwd_kernel<3><<<grid, kRmThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil,
-                                                            out_depth, D, H, W, S_h, S_w, P, tiles_x);
-    else if (min_blocks == 4)
-        raymarch_fwd_kernel<4><<<grid, kRmThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil,
-                                                            out_depth, D, H, W, S_h, S_w, P, tiles_x);
-    else
-        raymarch_fwd_kernel<2><<<grid, kRmThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil,
-                                                            out_depth, D, H, W, S_h, S_w, P, tiles_x);
+    // min_blocks counts 256-thread equivalents: the kernels are built for min_blocks * 8 resident warps per SM
+#define FORGE_K1_LAUNCH(WX, WY)                                                                                            \
+    do {                                                                                                                   \
+        constexpr int kW = WX * WY;                                                                                        \
+        if (min_blocks == 3)                                                                                               \
+            raymarch_fwd_kernel<24 / kW, WX, WY><<<grid, 32 * kW, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil, \
+                                                                          out_depth, D, H, W, S_h, S_w, P, tiles_x);       \
+        else if (min_blocks == 4)                                                                                          \
+            raymarch_fwd_kernel<32 / kW, WX, WY><<<grid, 32 * kW, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil, \
+                                                                          out_depth, D, H, W, S_h, S_w, P, tiles_x);       \
+        else                                                                                                               \
+            raymarch_fwd_kernel<16 / kW, WX, WY><<<grid, 32 * kW, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil, \
+                                                                          out_depth, D, H, W, S_h, S_w, P, tiles_x);       \
+    } while (0)
+    if (shape == 42) FORGE_K1_LAUNCH(4, 2);
+    else if (shape == 22) FORGE_K1_LAUNCH(2, 2);
+    else if (shape == 21) FORGE_K1_LAUNCH(2, 1);
+    else if (shape == 11) FORGE_K1_LAUNCH(1, 1);
+    else FORGE_K1_LAUNCH(4, 1);
+#undef FORGE_K1_LAUNCH
     return check_launch(fn);
 }
 
