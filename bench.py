@@ -389,7 +389,7 @@ def run_forge(args, rank, world, local_rank):
                      "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                      "algorithmic_bytes": algorithmic_bytes_k1(), "kernel_ms": k1_avg_s * 1e3,
                      "fp32_tflops": rays * CFG['n_pts'] * FLOPS_PER_SAMPLE / k1_avg_s / 1e12,
-                     "note": "K1 is bound by the L1 data pipe (register write-back of the gathered corners, ncu 72 %), not by "
+                     "note": "K1 is bound by the L1 data pipe (register write-back of the gathered corners, ncu 82 %), not by "
                              "HBM (SURVEY 8d: 82 FLOP/B); bytes are the distinct-volume figure; see roofline_rotate for the "
                              "HBM-bound kernel of the path"},
         "roofline_rotate": {"bound": "hbm", "kernel": "rotate_fwd_kernel (K2, %d view-volumes of 128x%d^3, channels-last)"
