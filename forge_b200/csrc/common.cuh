@@ -12,6 +12,11 @@ namespace forge {
 void set_error(const std::string& msg);
 int fail(const char* fn, const std::string& msg);
 int check_launch(const char* fn);
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device (function attributes are per device; a
+// process may drive several).  Remembers what was set per (kernel, device); returns 0 or a fail() code.
+int ensure_dynamic_smem(const char* fn, const void* kernel, size_t bytes);
+// Multiprocessor count of the current device (cached per device); 0 + error string on failure.
+int current_sm_count(const char* fn);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

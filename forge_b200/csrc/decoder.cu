@@ -302,13 +302,7 @@ extern "C" int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float*
     if (N > 65535) return fail(fn, "more than 65535 images in one launch");
     if (!aligned16(x_nhwc) || !aligned16(wpack)) return fail(fn, "x_nhwc / wpack must be 16-byte aligned");
     const size_t smem = sizeof(float) * kDecSmemFloats;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(decoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) return fail(fn, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-        attr_set = true;
-    }
+    if (int rc = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(decoder_fwd_kernel), smem)) return rc;
     const int tiles_x = (2 * S_w + TOX - 1) / TOX, tiles_y = (2 * S_h + TOY - 1) / TOY;
     dim3 grid(tiles_x * tiles_y, N);
     decoder_fwd_kernel<<<grid, kDecThreads, smem, static_cast<cudaStream_t>(stream)>>>(x_nhwc, wpack, rgb_nchw, sign_masks,

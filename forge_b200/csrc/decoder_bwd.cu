@@ -280,13 +280,7 @@ extern "C" int forge_decoder_bwd_data(const float* g_rgb_nchw, const unsigned* m
     if (N > 65535) return fail(fn, "more than 65535 images in one launch");
     if (!aligned16(wpack_bwd) || !aligned16(g_x_nhwc)) return fail(fn, "wpack_bwd / g_x_nhwc must be 16-byte aligned");
     const size_t smem = sizeof(float) * kSmemFloats;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(decoder_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) return fail(fn, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-        attr_set = true;
-    }
+    if (int rc = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(decoder_bwd_data_kernel), smem)) return rc;
     const int tiles_x = (2 * S_w + TOX - 1) / TOX, tiles_y = (2 * S_h + TOY - 1) / TOY;
     dim3 grid(tiles_x * tiles_y, N);
     decoder_bwd_data_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(g_rgb_nchw, masks, wpack_bwd, g_x_nhwc,

@@ -488,18 +488,9 @@ extern "C" int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, floa
     const int tiles_x = (2 * S_w + TOX - 1) / TOX, tiles_y = (2 * S_h + TOY - 1) / TOY;
     const long long total = static_cast<long long>(N) * tiles_x * tiles_y;
     if (total > 0x7fffffffLL) return fail(fn, "too many tiles for one launch");
-    static thread_local int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(decoder_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        if (e != cudaSuccess) {
-            sm_count = 0;
-            return fail(fn, std::string("device setup: ") + cudaGetErrorString(e));
-        }
-    }
+    if (int rc = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(decoder_tc_kernel), SM_TOTAL)) return rc;
+    const int sm_count = current_sm_count(fn);
+    if (sm_count <= 0) return 1;
     int ctas = 2 * sm_count;                       // persistent: two resident CTAs per SM
     if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
     if (total < ctas) ctas = static_cast<int>(total);
@@ -517,8 +508,7 @@ extern "C" int forge_umma_probe(const void* image, int image_bytes, unsigned a_o
     if (!image || !out) return fail(fn, "null pointer");
     if (image_bytes <= 0 || image_bytes % 16 || image_bytes > 200 * 1024) return fail(fn, "image_bytes must be a multiple of 16, <= 200 KiB");
     if ((a_off | a_lbo | a_sbo | b_off | b_lbo | b_sbo) & 15u) return fail(fn, "offsets must be multiples of 16 bytes");
-    cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, image_bytes);
-    if (e != cudaSuccess) return fail(fn, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    if (int rc = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(umma_probe_kernel), image_bytes)) return rc;
     umma_probe_kernel<<<1, 128, image_bytes, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const unsigned char*>(image), image_bytes, a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo, out);
     return check_launch(fn);

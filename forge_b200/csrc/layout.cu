@@ -1,4 +1,7 @@
 // libforge_b200: error plumbing, [n][C][S] <-> [n][S][C] re-layout kernels, sampler test hook.
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace forge {
@@ -16,6 +19,59 @@ int check_launch(const char* fn) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(fn, std::string("CUDA launch failed: ") + cudaGetErrorString(e));
     return 0;
+}
+
+namespace {
+struct SmemOptIn {
+    const void* kernel;
+    int device;
+    size_t bytes;
+};
+std::mutex g_attr_mutex;
+std::vector<SmemOptIn> g_smem_optin;
+std::vector<int> g_sm_count;     // indexed by device
+}  // namespace
+
+int ensure_dynamic_smem(const char* fn, const void* kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(fn, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    for (SmemOptIn& o : g_smem_optin) {
+        if (o.kernel == kernel && o.device == dev) {
+            if (o.bytes >= bytes) return 0;
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+            if (e != cudaSuccess) return fail(fn, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+            o.bytes = bytes;
+            return 0;
+        }
+    }
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) return fail(fn, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    g_smem_optin.push_back({kernel, dev, bytes});
+    return 0;
+}
+
+int current_sm_count(const char* fn) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        fail(fn, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+        return 0;
+    }
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    if (dev >= static_cast<int>(g_sm_count.size())) g_sm_count.resize(dev + 1, 0);
+    if (g_sm_count[dev] == 0) {
+        int n = 0;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess || n <= 0) {
+            fail(fn, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(e));
+            return 0;
+        }
+        g_sm_count[dev] = n;
+    }
+    return g_sm_count[dev];
 }
 
 // ---- transposes ---------------------------------------------------------------------------------
@@ -254,12 +310,7 @@ extern "C" int forge_pack_volume(const float* feat, int feat_channels_last, cons
     if (!aligned16(feat_pad) || (feat_channels_last && !aligned16(feat))) return fail(fn, "feat_pad / feat must be 16-byte aligned");
     const size_t smem = sizeof(float) * (kPackRows * (W * 17 + 2) + (kPackRows + 1) * (W + 2));
     if (smem > 200 * 1024) return fail(fn, "volume rows longer than 360 voxels are not supported");
-    static thread_local size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(pack_volume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return fail(fn, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-        smem_set = smem;
-    }
+    if (int rc = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(pack_volume_kernel), smem)) return rc;
     const int ygroups = (H + 2 + kPackRows - 1) / kPackRows;
     dim3 grid((D + 2) * ygroups, V);
     pack_volume_kernel<<<grid, kPackThreads, smem, static_cast<cudaStream_t>(stream)>>>(
