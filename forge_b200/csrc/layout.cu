@@ -33,7 +33,7 @@ std::vector<int> g_sm_count;     // indexed by device
 }  // namespace
 
 int ensure_dynamic_smem(const char* fn, const void* kernel, size_t bytes) {
-    if (bytes <= 48 * 1024) return 0;
+    if (bytes + 2048 <= 48 * 1024) return 0;      // static shared memory of the kernel counts against the 48 KB default too
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return fail(fn, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
