@@ -13,7 +13,7 @@
 //
 // Forward mapping: 2 lanes per ray, lane c owns feature channels 8c..8c+7 and fetches each corner
 // with one 256-bit load (LDG.E.256); a warp marches a 4x4 pixel patch (neighbouring rays are ~0.5
-// voxel apart, so their corner reads share 128-byte lines), a 256-thread CTA a 16x8 pixel tile.
+// voxel apart, so their corner reads share 128-byte lines), a 128-thread CTA a 16x4 pixel tile.
 // The two lanes split the density planes (dz = c) and combine with one xor-shuffle.  Samples outside
 // the exact ray/volume slab are skipped: under zeros padding they contribute exactly 0 and multiply
 // the transmittance by exactly 1.
@@ -233,11 +233,12 @@ raymarch_fwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
 // the 12 camera floats of the view.
 //
 // Same mapping and packed inputs as the forward kernel (2 lanes per ray, 256-bit corner loads, density
-// quads, 16x8 pixel tile per CTA).  grad_feat goes to a volume in feat_pad layout, grad_dens to a
+// quads, 16x4 pixel tile per CTA).  grad_feat goes to a volume in feat_pad layout, grad_dens to a
 // zero-bordered [V][D+2][H+2][W+2] volume, so neither scatter needs bounds predicates.
-constexpr int kRaysPerCta = kRmThreads / 2;
+constexpr int kBwThreads = 128;                 // 4 warps = 16x4 pixel tile (finer CTAs balance better than 16x8)
+constexpr int kRaysPerCta = kBwThreads / 2;
 
-__global__ void __launch_bounds__(kRmThreads, 2)
+__global__ void __launch_bounds__(kBwThreads, 4)
 raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict__ dens_quad,
                     const int* __restrict__ view2vol, const float* __restrict__ cam12, const float* __restrict__ zs_g,
                     const float* __restrict__ g_feat, const float* __restrict__ g_sil,
@@ -246,8 +247,8 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
                     int D, int H, int W, int Sh, int Sw, int P, int tiles_x) {
     __shared__ float zs[kMaxP];
     __shared__ float cam[12];
-    __shared__ float red[12 * (kRmThreads / 32)];
-    // per-CTA stash [P][3][128 rays] in the caller's workspace (L2-resident between the two passes);
+    __shared__ float red[12 * (kBwThreads / 32)];
+    // per-CTA stash [P][3][64 rays] in the caller's workspace (L2-resident between the two passes);
     // keeping it out of shared memory leaves the whole unified L1 to the corner gathers
     float* stash = workspace + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * P * 3 * kRaysPerCta;
     // heavy-first schedule, as in the forward kernel: views interleaved, tiles ranked centre-out
@@ -255,7 +256,7 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
     const int rank = order / n_views, n = order - rank * n_views;
     const int ty = centre_out(rank / tiles_x, tiles_y), tx = centre_out(rank % tiles_x, tiles_x);
 
-    for (int k = threadIdx.x; k < P; k += kRmThreads) zs[k] = zs_g[k];
+    for (int k = threadIdx.x; k < P; k += kBwThreads) zs[k] = zs_g[k];
     if (threadIdx.x < 12) cam[threadIdx.x] = cam12[n * 12 + threadIdx.x];
     __syncthreads();
 
@@ -263,7 +264,7 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = lane & 1, q = lane >> 1, ray = threadIdx.x >> 1;
     const int j = tx * 16 + (warp & 3) * 4 + (q & 3);
-    const int i = ty * 8 + (warp >> 2) * 4 + (q >> 2);
+    const int i = ty * 4 + (q >> 2);
     const bool valid = (i < Sh) && (j < Sw);
     Ray r = make_ray(cam, i, j, zs, P, D, H, W);
     if (!valid) r.k1 = 0;
@@ -423,13 +424,13 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
             float x = valid ? g12[e] : 0.f;
 #pragma unroll
             for (int s = 16; s >= 1; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
-            if (lane == 0) red[e * (kRmThreads / 32) + warp] = x;
+            if (lane == 0) red[e * (kBwThreads / 32) + warp] = x;
         }
         __syncthreads();
         if (threadIdx.x < 12) {
             float x = 0.f;
 #pragma unroll
-            for (int w = 0; w < kRmThreads / 32; ++w) x += red[threadIdx.x * (kRmThreads / 32) + w];
+            for (int w = 0; w < kBwThreads / 32; ++w) x += red[threadIdx.x * (kBwThreads / 32) + w];
             atomicAdd(grad_cam + n * 12 + threadIdx.x, x);
         }
     }
@@ -496,7 +497,7 @@ extern "C" int forge_raymarch_fwd(const float* feat_pad, const float* dens_quad,
 extern "C" long long forge_raymarch_bwd_workspace(int N, int S_h, int S_w, int P) {
     using namespace forge;
     if (N <= 0 || S_h <= 0 || S_w <= 0 || P <= 0) return 0;
-    const long long tiles = static_cast<long long>((S_w + 15) / 16) * ((S_h + 7) / 8);
+    const long long tiles = static_cast<long long>((S_w + 15) / 16) * ((S_h + 3) / 4);
     return tiles * N * P * 3 * kRaysPerCta * static_cast<long long>(sizeof(float));
 }
 
@@ -515,9 +516,9 @@ extern "C" int forge_raymarch_bwd(const float* feat_pad, const float* dens_quad,
     if ((reinterpret_cast<uintptr_t>(feat_pad) & 31u) || !aligned16(dens_quad) || !aligned16(g_feat) ||
         (grad_feat_pad && !aligned16(grad_feat_pad)))
         return fail(fn, "feat_pad must be 32-byte aligned, dens_quad / g_feat / grad_feat_pad 16-byte aligned");
-    const int tiles_x = (S_w + 15) / 16, tiles_y = (S_h + 7) / 8;
+    const int tiles_x = (S_w + 15) / 16, tiles_y = (S_h + 3) / 4;
     dim3 grid(tiles_x * tiles_y, N);
-    raymarch_bwd_kernel<<<grid, kRmThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    raymarch_bwd_kernel<<<grid, kBwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         feat_pad, reinterpret_cast<const float4*>(dens_quad), view2vol, cam12, zs, g_feat, g_sil, g_depth, grad_feat_pad,
         grad_dens_pad, grad_cam12, workspace, D, H, W, S_h, S_w, P, tiles_x);
     return check_launch(fn);
