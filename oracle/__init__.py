@@ -3,7 +3,10 @@
 CPU (and, for timing only, CUDA-eager) restatement of the reference algorithm for the FORGE
 render / rotate hot path.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; ``forge_b200/``
-never does, and the product path raises if its CUDA library is missing.
+never does (``tests/test_abi.py`` greps the product tree), and the product path raises if its CUDA
+library is missing.  The development benches under ``tools/`` (``--ref`` columns of bench_kernels.py,
+refine_bench.py, model_bench.py) time it on the GPU as the REFERENCE arm SURVEY 8d asks for -- the
+denominator of the "x the reference GPU renderer" figures -- never as part of a forge_b200 measurement.
 
 Layout
   p3d_standin/pytorch3d/   stand-in for the slice of PyTorch3D 0.7.0 the reference imports
