@@ -5,7 +5,7 @@
 // fetches of an output voxel are contiguous C*4-byte runs (512 B for C = 128) and the output write
 // is one contiguous run -- every HBM byte moved is an algorithmic byte.  HBM-bound.
 //
-// Work mapping: a CTA owns a compact 8x8x4 block of output voxels.  Phase 1: one thread per voxel
+// Work mapping: a CTA owns a compact block of output voxels (8x4x4 by default, see forge_rotate_fwd).  Phase 1: one thread per voxel
 // evaluates the sample position once and leaves the 8 corner offsets + weights in shared memory
 // (out-of-volume corners get weight 0 and a clamped offset, so phase 2 has no predicates).
 // Phase 2: one thread per (voxel, channel vector): 4 broadcast LDS.128, 8 coalesced LDG.128,
@@ -24,7 +24,9 @@ struct TileShape {
     int tx, ty, tz;
 };
 __host__ __device__ constexpr TileShape tile_shape(int id) {
-    return id == 1 ? TileShape{16, 4, 4} : id == 2 ? TileShape{4, 8, 8} : id == 3 ? TileShape{16, 16, 1} : id == 4 ? TileShape{32, 8, 1} : TileShape{8, 8, 4};
+    return id == 1 ? TileShape{16, 4, 4} : id == 2 ? TileShape{4, 8, 8} : id == 3 ? TileShape{16, 16, 1} : id == 4 ? TileShape{32, 8, 1}
+         : id == 5 ? TileShape{8, 8, 2} : id == 6 ? TileShape{8, 4, 4} : id == 7 ? TileShape{8, 4, 2} : id == 8 ? TileShape{4, 4, 4}
+         : TileShape{8, 8, 4};     // 5, 6: half tiles (128 voxels), 7, 8: quarter tiles
 }
 static_assert(kTileVox == kRotThreads, "phase 1 maps one thread to one voxel");
 
@@ -81,7 +83,7 @@ __device__ __forceinline__ void rotate_phase1(RotTile& s, float (*frac)[6], cons
     __syncthreads();
     const int v = threadIdx.x;
     const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
-    if (w >= W || h >= H || d >= D) {
+    if (v >= kTx * kTy * kTz || w >= W || h >= H || d >= D) {     // half tiles leave the upper threads without a voxel
         s.out[v] = -1;
     } else {
         s.out[v] = (d * H + h) * W + w;
@@ -125,8 +127,9 @@ rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
     const VecT* src = in + static_cast<long long>(job.src) * vol * CU;
     VecT* dst = out + static_cast<long long>(job.dst) * vol * CU;
 
+    constexpr int kVox = kTx * kTy * kTz;
     if (job.kind == 1) {   // view-0 passthrough (models/rotate.py:141)
-        for (int e = threadIdx.x; e < kTileVox * CU; e += kRotThreads) {
+        for (int e = threadIdx.x; e < kVox * CU; e += kRotThreads) {
             const int v = e / CU, cu = e - v * CU;
             const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
             if (w >= W || h >= H || d >= D) continue;
@@ -138,7 +141,7 @@ rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
     rotate_phase1(s, nullptr, affine, m, gx, gy, gz, inv_max, D, H, W, tx, ty, tz, sh);
 
 #pragma unroll 2
-    for (int e = threadIdx.x; e < kTileVox * CU; e += kRotThreads) {
+    for (int e = threadIdx.x; e < kVox * CU; e += kRotThreads) {
         const int v = e / CU, cu = e - v * CU;
         const int o = s.out[v];
         if (o < 0) continue;
@@ -296,10 +299,18 @@ extern "C" int forge_rotate_fwd(const float* vox_cl, const float* affine12, cons
     const char* fn = "forge_rotate_fwd";
     if (int e = rotate_check(fn, vox_cl, affine12, jobs, gx, gy, gz, grid_coord_max, M, C, D, H, W)) return e;
     if (!out_cl) return fail(fn, "null pointer");
-    static const int shape_id = [] {        // tuning knobs (development)
+    static const int shape_env = [] {       // tuning knobs (development)
         const char* e = getenv("FORGE_K2_SHAPE");
-        return e ? atoi(e) : 0;
+        return e ? atoi(e) : -1;
     }();
+    // default: half tiles (8x4x4 voxels per 256-thread CTA) -- twice the CTAs of a full tile halve the tail of the
+    // launch (cfg-2: 4.3 -> 8.6 waves, 61.9 -> 66.0 % of the HBM peak; cfg-4: 71.2 -> 72.4 %); quarter tiles when even
+    // those do not fill one wave of the GPU (cfg-1: 0.029 -> 0.016 ms)
+    int shape_id = shape_env;
+    if (shape_id < 0) {
+        const long long half_tiles = static_cast<long long>((W + 7) / 8) * ((H + 3) / 4) * ((D + 3) / 4) * M;
+        shape_id = half_tiles < 1184 ? 7 : 6;
+    }
     static const bool stream_st = [] {
         const char* e = getenv("FORGE_K2_STREAM");
         return e ? atoi(e) != 0 : false;
@@ -321,6 +332,10 @@ extern "C" int forge_rotate_fwd(const float* vox_cl, const float* affine12, cons
                 case 2: FORGE_K2_LAUNCH(2, true); break;
                 case 3: FORGE_K2_LAUNCH(3, true); break;
                 case 4: FORGE_K2_LAUNCH(4, true); break;
+                case 5: FORGE_K2_LAUNCH(5, true); break;
+                case 6: FORGE_K2_LAUNCH(6, true); break;
+                case 7: FORGE_K2_LAUNCH(7, true); break;
+                case 8: FORGE_K2_LAUNCH(8, true); break;
                 default: FORGE_K2_LAUNCH(0, true); break;
             }
         } else {
@@ -329,6 +344,10 @@ extern "C" int forge_rotate_fwd(const float* vox_cl, const float* affine12, cons
                 case 2: FORGE_K2_LAUNCH(2, false); break;
                 case 3: FORGE_K2_LAUNCH(3, false); break;
                 case 4: FORGE_K2_LAUNCH(4, false); break;
+                case 5: FORGE_K2_LAUNCH(5, false); break;
+                case 6: FORGE_K2_LAUNCH(6, false); break;
+                case 7: FORGE_K2_LAUNCH(7, false); break;
+                case 8: FORGE_K2_LAUNCH(8, false); break;
                 default: FORGE_K2_LAUNCH(0, false); break;
             }
         }
