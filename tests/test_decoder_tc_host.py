@@ -133,3 +133,31 @@ def test_weight_pack_and_index_plan_replay():
     scale = max(1.0, ref.abs().max().item())
     assert (out - ref).abs().max().item() <= 4e-3 * scale
     assert (out - ref32).abs().max().item() <= 6e-2 * scale
+
+
+def test_backward_weight_pack_reproduces_autograd_input_gradient():
+    """pack_decoder_bwd_weights (flipped / transposed filters, folded BN scales) + the sign masks are all the backward kernel
+    uses: chaining plain correlations over the pack reproduces autograd's d relu(conv_rgb(x)) / d x on the CPU."""
+    torch.manual_seed(1)
+    m = VolRender(syn.make_config(img_size=32, n_pts_per_ray=8)).eval()
+    for mod in m.conv_rgb:
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.3)
+            mod.running_var.uniform_(0.5, 2.0)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.2)
+    pack = ops.pack_decoder_bwd_weights(m.conv_rgb)
+    w3b, w2b, wd = pack[:600].view(5, 5, 3, 8), pack[600:3800].view(5, 5, 8, 16), pack[3800:].view(6, 6, 16, 16)
+    x = torch.randn(2, 16, 16, 16, requires_grad=True)
+    ct, bn1, _, c2, bn2, _, c3 = m.conv_rgb
+    pre1 = bn1(ct(x.permute(0, 3, 1, 2)))
+    pre2 = bn2(c2(F.leaky_relu(pre1, 0.01)))
+    pre3 = c3(F.leaky_relu(pre2, 0.01))
+    g = torch.randn_like(pre3)
+    F.relu(pre3).backward(g)
+    with torch.no_grad():
+        g3 = g * (pre3 > 0)
+        g2 = F.conv2d(g3, w3b.permute(3, 2, 0, 1), padding=2) * torch.where(pre2 > 0, 1.0, 0.01)
+        g1 = F.conv2d(g2, w2b.permute(3, 2, 0, 1), padding=2) * torch.where(pre1 > 0, 1.0, 0.01)
+        gx = F.conv2d(g1, wd.permute(3, 2, 0, 1), stride=2, padding=2).permute(0, 2, 3, 1)
+    assert (gx - x.grad).abs().max().item() <= 1e-6 * max(1.0, x.grad.abs().max().item())
