@@ -189,8 +189,8 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
                   float inv_max, const VecT* __restrict__ g_out, VecT* __restrict__ grad_in,
                   float* __restrict__ grad_aff, int CU, int D, int H, int W, int tiles_x, int tiles_y) {
     __shared__ __align__(16) RotTile s;
-    constexpr TileShape sh = tile_shape(0);
-    constexpr int kTx = sh.tx, kTy = sh.ty, kTz = sh.tz;
+    constexpr TileShape sh = tile_shape(6);           // half tiles, like the forward kernel
+    constexpr int kTx = sh.tx, kTy = sh.ty, kTz = sh.tz, kVox = kTx * kTy * kTz;
     __shared__ float frac[kTileVox][6];
     __shared__ float red[12][kRotThreads / 32];
     const int m = blockIdx.y;
@@ -205,7 +205,7 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
 
     if (job.kind == 1) {
         if (!gin) return;
-        for (int e = threadIdx.x; e < kTileVox * CU; e += kRotThreads) {
+        for (int e = threadIdx.x; e < kVox * CU; e += kRotThreads) {
             const int v = e / CU, cu = e - v * CU;
             const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
             if (w >= W || h >= H || d >= D) continue;
@@ -223,7 +223,7 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
 #pragma unroll
     for (int e = 0; e < 12; ++e) ga[e] = 0.f;
 
-    for (int e = threadIdx.x; e < kTileVox * CU; e += kRotThreads) {
+    for (int e = threadIdx.x; e < kVox * CU; e += kRotThreads) {
         const int v = e / CU, cu = e - v * CU;
         const int o = s.out[v];
         if (o < 0) continue;
@@ -370,7 +370,7 @@ extern "C" int forge_rotate_bwd(const float* vox_cl, const float* affine12, cons
     if (int e = rotate_check(fn, vox_cl, affine12, jobs, gx, gy, gz, grid_coord_max, M, C, D, H, W)) return e;
     if (!g_out_cl) return fail(fn, "null pointer");
     if (!grad_vox_cl && !grad_affine12) return 0;
-    const TileShape sh = tile_shape(0);
+    const TileShape sh = tile_shape(6);
     const int tiles_x = (W + sh.tx - 1) / sh.tx, tiles_y = (H + sh.ty - 1) / sh.ty, tiles_z = (D + sh.tz - 1) / sh.tz;
     dim3 grid(tiles_x * tiles_y * tiles_z, M);
     const float inv_max = 1.0f / grid_coord_max;
