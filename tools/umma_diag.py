@@ -15,10 +15,10 @@ def expected(img, off, kstride, gstride, rows):
 
 def main():
     torch.manual_seed(0)
-    nbytes = 48 * 1024
+    nbytes = 96 * 1024
     img = (torch.randint(-8, 9, (nbytes // 2,)).float() / 4).to(torch.bfloat16)
     dimg = img.view(torch.uint8).cuda()
-    b_off = 40 * 1024
+    b_off = 88 * 1024
     for (a_off, a_lbo, a_sbo) in [(0, 2048, 128), (16, 2048, 128), (128, 2048, 128), (16 * 45, 6912, 128), (16 * 83, 640, 128),
                                   (16 * 164, 16, 128), (0, 128, 256), (0, 256, 128)]:
         try:
