@@ -37,9 +37,13 @@ _SIGNATURES = {
     "forge_upsample2x_fwd": (_c.c_int, [_F, _F, _F, _F, _I, _I, _I, _F]),
     "forge_upsample2x_bwd": (_c.c_int, [_F, _F, _F, _F, _I, _I, _I, _F]),
     "forge_pose_affine_fwd": (_c.c_int, [_F, _I, _I, _F, _F, _F, _F]),
+    "forge_gru_gate_fwd": (_c.c_int, [_F, _I, _F, _c.c_longlong, _F, _c.c_longlong, _F, _I, _I, _I, _I, _F]),
+    "forge_gru_gate_bwd": (_c.c_int, [_F, _F, _I, _F, _c.c_longlong, _F, _F, _F, _I, _I, _I, _I, _F]),
+    "forge_gru_out_fwd": (_c.c_int, [_F, _F, _I, _F, _c.c_longlong, _F, _I, _I, _I, _I, _F]),
+    "forge_gru_out_bwd": (_c.c_int, [_F, _F, _F, _I, _F, _c.c_longlong, _F, _F, _F, _I, _I, _I, _I, _F]),
     "forge_sample_points": (_c.c_int, [_F, _I, _I, _I, _I, _I, _F, _F, _F]),
 }
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _lock = threading.Lock()
 _lib = None

@@ -9,6 +9,8 @@ cuDNN; inputs arriving channels-last (K2's output layout) are consumed as ``chan
 import torch
 import torch.nn as nn
 
+from .. import ops
+
 
 def _conv_bn_act(cin, cout):
     return [nn.Conv3d(cin, cout, 3, padding=1), nn.BatchNorm3d(cout), nn.LeakyReLU(inplace=True)]
@@ -23,11 +25,16 @@ class ConvGRUCell_3D(nn.Module):
         width = input_size + hidden_size
         self.conv_gate = nn.Conv3d(width, 2 * hidden_size, 3, padding=1)     # update | reset
         self.out_gate = nn.Conv3d(width, hidden_size, 3, padding=1)          # candidate state
+        self.fused_gates = True
 
     def forward(self, x, prev_state=None):
         h = prev_state
         if h is None:
             h = x.new_zeros((x.shape[0], self.hidden_size) + tuple(x.shape[2:]))
+        if self.fused_gates and x.is_cuda:
+            # the elementwise chain between the two convs as two launches (forge_gru_gate_* / forge_gru_out_*)
+            g = self.conv_gate(torch.cat((x, h), 1))
+            return ops.gru_out(self.out_gate(ops.gru_gate(g, h, x)), g, h)
         u, r = torch.sigmoid(self.conv_gate(torch.cat((x, h), 1))).split(self.hidden_size, dim=1)
         c = torch.tanh(self.out_gate(torch.cat((x, h * r), 1)))
         return h * (1 - u) + c * u

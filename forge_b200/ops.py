@@ -525,3 +525,115 @@ def upsample2x(a, b=None):
     _require_cuda(a, b)
     oa, ob = _Upsample2x.apply(_f32c(a), None if b is None else _f32c(b))
     return oa, (ob if b is not None else None)
+
+
+# ---- ConvGRU cell: fused elementwise stages -----------------------------------------------------------
+def _gru_layout(g):
+    """conv output [B,CC,D,H,W] -> (dense tensor, channels_last flag)"""
+    if g.is_contiguous(memory_format=torch.channels_last_3d) and not g.is_contiguous():
+        return g, 1
+    return (g if g.is_contiguous() else g.contiguous()), 0
+
+
+def _gru_fmt(cl):
+    return torch.channels_last_3d if cl else torch.contiguous_format
+
+
+def _gru_operand(t, cl):
+    """fp32 [B,C,D,H,W] whose inner dims are dense in the given layout (the batch stride is free) -> (tensor, batch stride)"""
+    if t.dtype != torch.float32:
+        t = t.float()
+    B, C, D, H, W = t.shape
+    want = (None, 1, H * W * C, W * C, C) if cl else (None, D * H * W, H * W, W, 1)
+    ok = all(t.shape[i] == 1 or t.stride(i) == want[i] for i in range(1, 5))
+    if not ok:
+        t = t.contiguous(memory_format=_gru_fmt(cl))
+    return t, (t.stride(0) if B > 1 else C * D * H * W)
+
+
+def _gru_dense(t, cl, dtype=torch.float32):
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous(memory_format=_gru_fmt(cl))
+
+
+class _GruGate(torch.autograd.Function):
+    """xhr = cat(x, h * sigmoid(g[:, C:])) in one launch."""
+
+    @staticmethod
+    def forward(ctx, g, h, x):
+        g, cl = _gru_layout(g)
+        B, C2, D, H, W = g.shape
+        C, S = C2 // 2, D * H * W
+        h, hbs = _gru_operand(h, cl)
+        x, xbs = _gru_operand(x, cl)
+        xhr = torch.empty(g.shape, dtype=torch.float32, device=g.device, memory_format=_gru_fmt(cl))
+        bf = int(g.dtype == torch.bfloat16)
+        with torch.cuda.device(g.device):
+            _lib.call("forge_gru_gate_fwd", _ptr(g), bf, _ptr(h), hbs, _ptr(x), xbs, _ptr(xhr), cl, B, C, S, _stream(g))
+        ctx.save_for_backward(g, h)
+        ctx.meta = (cl, B, C, S, hbs, bf)
+        return xhr
+
+    @staticmethod
+    def backward(ctx, d_xhr):
+        g, h = ctx.saved_tensors
+        cl, B, C, S, hbs, bf = ctx.meta
+        d_xhr = _gru_dense(d_xhr, cl)
+        dg = torch.empty_like(g)
+        dh = torch.empty((B, C) + tuple(g.shape[2:]), dtype=torch.float32, device=g.device, memory_format=_gru_fmt(cl))
+        dx = torch.empty_like(dh)
+        with torch.cuda.device(g.device):
+            _lib.call("forge_gru_gate_bwd", _ptr(d_xhr), _ptr(g), bf, _ptr(h), hbs, _ptr(dg), _ptr(dh), _ptr(dx), cl, B, C, S,
+                      _stream(g))
+        return dg, dh, dx
+
+
+class _GruOut(torch.autograd.Function):
+    """h' = h (1 - u) + tanh(o) u with u = sigmoid(g[:, :C]) in one launch."""
+
+    @staticmethod
+    def forward(ctx, o, g, h):
+        g, cl = _gru_layout(g)
+        B, C2, D, H, W = g.shape
+        C, S = C2 // 2, D * H * W
+        o = _gru_dense(o, cl, g.dtype)
+        h, hbs = _gru_operand(h, cl)
+        hn = torch.empty(o.shape, dtype=torch.float32, device=g.device, memory_format=_gru_fmt(cl))
+        bf = int(g.dtype == torch.bfloat16)
+        with torch.cuda.device(g.device):
+            _lib.call("forge_gru_out_fwd", _ptr(o), _ptr(g), bf, _ptr(h), hbs, _ptr(hn), cl, B, C, S, _stream(g))
+        ctx.save_for_backward(o, g, h)
+        ctx.meta = (cl, B, C, S, hbs, bf)
+        return hn
+
+    @staticmethod
+    def backward(ctx, d_hn):
+        o, g, h = ctx.saved_tensors
+        cl, B, C, S, hbs, bf = ctx.meta
+        d_hn = _gru_dense(d_hn, cl)
+        d_o = torch.empty_like(o)
+        dg = torch.empty_like(g)
+        dh = torch.empty(o.shape, dtype=torch.float32, device=g.device, memory_format=_gru_fmt(cl))
+        with torch.cuda.device(g.device):
+            _lib.call("forge_gru_out_bwd", _ptr(d_hn), _ptr(o), _ptr(g), bf, _ptr(h), hbs, _ptr(d_o), _ptr(dg), _ptr(dh), cl, B, C, S,
+                      _stream(g))
+        return d_o, dg, dh
+
+
+def gru_gate(g, h, x):
+    """g = conv_gate(cat(x, h)) [B,2C,D,H,W] (fp32 or bf16), h, x [B,C,D,H,W] -> cat(x, h * sigmoid(g[:, C:])) fp32
+    (reference models/fusion.py:31-33: sigmoid, split, mul, cat)."""
+    _require_cuda(g, h, x)
+    if g.dtype not in (torch.float32, torch.bfloat16):
+        g = g.float()
+    return _GruGate.apply(g, h.float(), x.float())
+
+
+def gru_out(o, g, h):
+    """o = out_gate(cat(x, h r)) [B,C,D,H,W], g as above, h -> h (1 - u) + tanh(o) u, u = sigmoid(g[:, :C])
+    (reference models/fusion.py:33-35)."""
+    _require_cuda(o, g, h)
+    if g.dtype not in (torch.float32, torch.bfloat16):
+        g = g.float()
+    return _GruOut.apply(o.to(g.dtype), g, h.float())

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 11
+#define FORGE_ABI_VERSION 12
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -190,6 +190,25 @@ int forge_upsample2x_bwd(const float* g_dst0, const float* g_dst1, float* g_src0
  *   *singular_flag (optional, device int) is set to 1 when a pose is singular (its outputs are NaN). */
 int forge_pose_affine_fwd(const float* poses, int B, int t, float* affine12, float* pose_inv, int* singular_flag,
                           void* stream);
+
+/* ---- ConvGRU cell, elementwise stages (models/fusion.py:21-35) -----------------------------------
+ * The two convolutions of a cell stay cuDNN; the chain between them is two kernels forward and two backward:
+ *   gate:  xhr = cat(x, h * sigmoid(g[:, C:]))                      g = conv_gate(cat(x, h))  [B][2C][S]
+ *   out:   h'  = h (1 - u) + tanh(o) u,  u = sigmoid(g[:, :C])      o = out_gate(xhr)         [B][C][S]
+ * channels_last = 0: tensors are [B][CC][S]; 1: [B][S][CC] (channels_last_3d).  g, o and their gradients are fp32
+ * (bf16 flag 0) or bf16 (flag 1, autocast); h, x, xhr, h' and their gradients are fp32.  h and x may have their own
+ * batch stride (elements); every other tensor is dense.  S = D*H*W, B * 2C * S < 2^31.
+ * Backward: gate_bwd writes d_g[:, C:], d_h (= contribution through h*r), d_x and ZEROES d_g[:, :C]; out_bwd writes
+ * d_o, d_g[:, :C], d_h (= contribution through the lerp) and ZEROES d_g[:, C:] -- the caller adds the two d_g / d_h. */
+int forge_gru_gate_fwd(const void* g, int g_bf16, const float* h, long long h_batch_stride, const float* x,
+                       long long x_batch_stride, float* xhr, int channels_last, int B, int C, int S, void* stream);
+int forge_gru_gate_bwd(const float* d_xhr, const void* g, int g_bf16, const float* h, long long h_batch_stride, void* d_g,
+                       float* d_h, float* d_x, int channels_last, int B, int C, int S, void* stream);
+int forge_gru_out_fwd(const void* o, const void* g, int og_bf16, const float* h, long long h_batch_stride, float* h_new,
+                      int channels_last, int B, int C, int S, void* stream);
+int forge_gru_out_bwd(const float* d_h_new, const void* o, const void* g, int og_bf16, const float* h,
+                      long long h_batch_stride, void* d_o, void* d_g, float* d_h, int channels_last, int B, int C, int S,
+                      void* stream);
 
 /* ---- test hook: the index path of both samplers -------------------------------------------
  * For each normalised point pts[m] = (x, y, z) returns the base voxel (floor) index base[m] =
