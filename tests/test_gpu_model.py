@@ -89,3 +89,40 @@ def test_pose_estimator3d_variant_view_to_volume_table():
     assert torch.isfinite(rgb).all()
     # views 5..9 (all-view volume) differ from views 0..4 (partial-view volumes) of the same cameras
     assert (mask[:5] - mask[5:]).abs().max().item() > 0
+
+
+def test_pose_gradient_is_unchanged_by_prepare_for_pose_refinement():
+    """The refine-loop configuration (frozen weights -> decoder backward kernel, channels-last convs, fused GRU stages) yields the
+    same loss and the same gradient to the camera poses as the unprepared model."""
+    import copy
+    import torch.nn.functional as F
+    from forge_b200.models.model import sequence_from_distance
+    from forge_b200.refine import prepare_for_pose_refinement
+    torch.manual_seed(2)
+    cfg = syn.make_config(img_size=128, n_pts_per_ray=24, use_gt_pose=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = FORGE(cfg).to(DEV).eval()
+    model.encoder_3d.density_head[6].bias.data.fill_(0.05)
+    sample = syn.kubric_batch(1, n_views_all=5, img_size=128, seed=5)
+    with torch.no_grad():
+        feats = model.lift(sample['images'].to(DEV)).detach()
+    P0 = sample['cam_poses_cv2_canonicalized'][:, :5].to(DEV)
+    K = sample['K_cv2'][0].to(DEV)
+    tgt = torch.rand(5, 3, 128, 128, device=DEV)
+
+    def loss_and_grad(m):
+        P = P0.clone().requires_grad_(True)
+        E = torch.inverse(P[0])
+        feat, dens = m.reconstruct(feats, P, sequence_from_distance(P[:, :, :3, 3]))
+        rgb, mask, _ = m.render({'R': E[:, :3, :3], 'T': E[:, :3, 3], 'K': K.clone()}, feat, dens, return_origin_proj=True,
+                                view2vol=torch.zeros(5, dtype=torch.int32, device=DEV))
+        loss = F.mse_loss(rgb, tgt) + mask.mean()
+        loss.backward()
+        return loss.item(), P.grad.clone()
+
+    l0, g0 = loss_and_grad(model)
+    l1, g1 = loss_and_grad(prepare_for_pose_refinement(copy.deepcopy(model)))
+    assert g0.abs().max().item() > 0
+    assert abs(l0 - l1) <= 1e-5 * max(1.0, abs(l0))
+    assert (g0 - g1).abs().max().item() <= 2e-3 * g0.abs().max().item()
