@@ -98,6 +98,8 @@ def test_pose_gradient_is_unchanged_by_prepare_for_pose_refinement():
     import torch.nn.functional as F
     from forge_b200.models.model import sequence_from_distance
     from forge_b200.refine import prepare_for_pose_refinement
+    torch.backends.cudnn.allow_tf32 = False          # channels-last vs NCDHW convs pick different kernels: compare in strict fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(2)
     cfg = syn.make_config(img_size=128, n_pts_per_ray=24, use_gt_pose=True)
     with warnings.catch_warnings():
