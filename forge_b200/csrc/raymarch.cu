@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(32 * kWX * kWY, kMinBlocks)
 raymarch_fwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict__ dens_quad,
                     const int* __restrict__ view2vol, const float* __restrict__ cam12, const float* __restrict__ zs_g,
                     float* __restrict__ out_feat, float* __restrict__ out_sil, float* __restrict__ out_depth, int D,
-                    int H, int W, int Sh, int Sw, int P, int tiles_x) {
+                    int H, int W, int Sh, int Sw, int P, int tiles_x, int interleave) {
     __shared__ float zs[kMaxP];
     __shared__ float cam[12];
     // Heavy-first schedule: CTAs are dispatched in (blockIdx.x, then blockIdx.y) order; map that order to
@@ -137,7 +137,9 @@ raymarch_fwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
     // middle of the volume) start first and the last wave consists of the short border tiles (ncu: SMs were idle
     // 9 % of the launch with the row-major order).
     const int order = blockIdx.y * gridDim.x + blockIdx.x, n_views = gridDim.y, tiles_y = gridDim.x / tiles_x;
-    const int rank = order / n_views, n = order - rank * n_views;
+    // views are interleaved only while all packed volumes fit in L2 together (host decision); otherwise view by view
+    const int rank = interleave ? order / n_views : static_cast<int>(blockIdx.x);
+    const int n = interleave ? order - rank * n_views : static_cast<int>(blockIdx.y);
     const int ri = rank / tiles_x, ci = rank - ri * tiles_x;
     const int ty = centre_out(ri, tiles_y), tx = centre_out(ci, tiles_x);
     for (int k = threadIdx.x; k < P; k += 32 * kWX * kWY) zs[k] = zs_g[k];
@@ -244,7 +246,7 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
                     const float* __restrict__ g_feat, const float* __restrict__ g_sil,
                     const float* __restrict__ g_depth, float* __restrict__ grad_feat_pad,
                     float* __restrict__ grad_dens_pad, float* __restrict__ grad_cam, float* __restrict__ workspace,
-                    int D, int H, int W, int Sh, int Sw, int P, int tiles_x) {
+                    int D, int H, int W, int Sh, int Sw, int P, int tiles_x, int interleave) {
     __shared__ float zs[kMaxP];
     __shared__ float cam[12];
     __shared__ float red[12 * (kBwThreads / 32)];
@@ -253,7 +255,8 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
     float* stash = workspace + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * P * 3 * kRaysPerCta;
     // heavy-first schedule, as in the forward kernel: views interleaved, tiles ranked centre-out
     const int order = blockIdx.y * gridDim.x + blockIdx.x, n_views = gridDim.y, tiles_y = gridDim.x / tiles_x;
-    const int rank = order / n_views, n = order - rank * n_views;
+    const int rank = interleave ? order / n_views : static_cast<int>(blockIdx.x);
+    const int n = interleave ? order - rank * n_views : static_cast<int>(blockIdx.y);
     const int ty = centre_out(rank / tiles_x, tiles_y), tx = centre_out(rank % tiles_x, tiles_x);
 
     for (int k = threadIdx.x; k < P; k += kBwThreads) zs[k] = zs_g[k];
@@ -445,6 +448,13 @@ static int raymarch_check(const char* fn, int N, int V, int D, int H, int W, int
     return 0;
 }
 
+// Interleave the views in the dispatch order only while all packed feature volumes fit in L2 together (cfg-2: 74 MB);
+// beyond that (cfg-4: 1.1 GB) a view-by-view order keeps one or two volumes hot at a time.
+inline int interleave_views(int V, int D, int H, int W) {
+    const long long bytes = static_cast<long long>(V) * (D + 2) * (H + 2) * (W + 2) * 64;
+    return bytes <= 96LL * 1024 * 1024;
+}
+
 }  // namespace forge
 
 extern "C" int forge_raymarch_fwd(const float* feat_pad, const float* dens_quad, const int* view2vol,
@@ -471,19 +481,20 @@ extern "C" int forge_raymarch_fwd(const float* feat_pad, const float* dens_quad,
     dim3 grid(tiles_x * tiles_y, N);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float4* dq = reinterpret_cast<const float4*>(dens_quad);
+    const int interleave = interleave_views(V, D, H, W);
     // min_blocks counts 256-thread equivalents: the kernels are built for min_blocks * 8 resident warps per SM
 #define FORGE_K1_LAUNCH(WX, WY)                                                                                            \
     do {                                                                                                                   \
         constexpr int kW = WX * WY;                                                                                        \
         if (min_blocks == 3)                                                                                               \
             raymarch_fwd_kernel<24 / kW, WX, WY><<<grid, 32 * kW, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil, \
-                                                                          out_depth, D, H, W, S_h, S_w, P, tiles_x);       \
+                                                                          out_depth, D, H, W, S_h, S_w, P, tiles_x, interleave); \
         else if (min_blocks == 4)                                                                                          \
             raymarch_fwd_kernel<32 / kW, WX, WY><<<grid, 32 * kW, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil, \
-                                                                          out_depth, D, H, W, S_h, S_w, P, tiles_x);       \
+                                                                          out_depth, D, H, W, S_h, S_w, P, tiles_x, interleave); \
         else                                                                                                               \
             raymarch_fwd_kernel<16 / kW, WX, WY><<<grid, 32 * kW, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, out_feat, out_sil, \
-                                                                          out_depth, D, H, W, S_h, S_w, P, tiles_x);       \
+                                                                          out_depth, D, H, W, S_h, S_w, P, tiles_x, interleave); \
     } while (0)
     if (shape == 42) FORGE_K1_LAUNCH(4, 2);
     else if (shape == 22) FORGE_K1_LAUNCH(2, 2);
@@ -520,6 +531,6 @@ extern "C" int forge_raymarch_bwd(const float* feat_pad, const float* dens_quad,
     dim3 grid(tiles_x * tiles_y, N);
     raymarch_bwd_kernel<<<grid, kBwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         feat_pad, reinterpret_cast<const float4*>(dens_quad), view2vol, cam12, zs, g_feat, g_sil, g_depth, grad_feat_pad,
-        grad_dens_pad, grad_cam12, workspace, D, H, W, S_h, S_w, P, tiles_x);
+        grad_dens_pad, grad_cam12, workspace, D, H, W, S_h, S_w, P, tiles_x, interleave_views(V, D, H, W));
     return check_launch(fn);
 }
