@@ -6,6 +6,7 @@ possible, or the ABI version differs, importing callers get a RuntimeError.
 import ctypes
 import os
 import threading
+import warnings
 
 from . import build as _build
 
@@ -69,6 +70,12 @@ def load():
                 raise RuntimeError(
                     "forge_b200: libforge_b200.so is missing and could not be built (%s). "
                     "The CUDA extension is mandatory; there is no CPU path." % e) from e
+            # a library exists but it is not the one these sources describe: refuse unless told otherwise
+            if os.environ.get("FORGE_ALLOW_STALE_LIB") != "1":
+                raise RuntimeError(
+                    "forge_b200: the sources changed but rebuilding libforge_b200.so failed (%s); refusing to load the "
+                    "stale library (set FORGE_ALLOW_STALE_LIB=1 to load it anyway)" % e) from e
+            warnings.warn("forge_b200: loading a STALE libforge_b200.so (rebuild failed: %s)" % e)
         try:
             lib = _c.CDLL(path)
         except OSError as e:

@@ -5,6 +5,7 @@
 The shared object lands in forge_b200/lib/ (git-ignored, but it travels to the GPU box with the
 repo snapshot).  ``-lineinfo`` keeps ncu's source page usable.
 """
+import fcntl
 import hashlib
 import os
 import shutil
@@ -41,24 +42,52 @@ def _digest():
     return h.hexdigest()
 
 
+def _up_to_date(digest):
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as fh:
+        return fh.read().strip() == digest
+
+
 def build(force=False, verbose=False):
-    """Compile if sources changed. Returns the path of the shared library."""
+    """Compile if sources changed. Returns the path of the shared library.
+
+    Safe under torchrun / DDP: the digest check and the compile run under an inter-process file lock, nvcc writes to a
+    temporary file that is renamed into place (a concurrent CDLL never sees a half-written library), and the stamp is
+    written after the rename."""
     os.makedirs(LIBDIR, exist_ok=True)
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
-        with open(STAMP) as fh:
-            if fh.read().strip() == digest:
+    if not force and _up_to_date(digest):
+        return LIB
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(digest):        # another rank built it while we waited
                 return LIB
-    cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
-           "-Xptxas", "-v" if verbose else "-O3", "-o", LIB, *_sources()]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libforge_b200.so (see stderr)")
-    with open(STAMP, "w") as fh:
-        fh.write(digest)
+            tmp = "%s.tmp.%d" % (LIB, os.getpid())
+            cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
+                   "-Xptxas", "-v" if verbose else "-O3", "-o", tmp, *_sources()]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libforge_b200.so (see stderr)")
+            if os.path.exists(STAMP):
+                os.remove(STAMP)                           # never a stamp that describes another library
+            os.replace(tmp, LIB)
+            with open(STAMP + ".tmp", "w") as fh:
+                fh.write(digest)
+            os.replace(STAMP + ".tmp", STAMP)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
+
+
+def stamp_matches_sources():
+    """True when the library on disk was built from the sources on disk."""
+    return _up_to_date(_digest())
 
 
 if __name__ == "__main__":

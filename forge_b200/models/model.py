@@ -36,15 +36,29 @@ def chose_selected(tensor, idxs):
     return torch.stack([tensor[i][idxs[i]] for i in range(len(idxs))])
 
 
-def _mat2quat(T):
-    """[n,4,4] -> [n,7] (w,x,y,z quaternion + translation); stand-in for reference utils/geo_utils.mat2quat
-    used only to return the ground-truth pose alongside the prediction."""
+def _mat2quat(T, eps=1e-6):
+    """[n,4,4] -> [n,7] (w,x,y,z quaternion + translation), same values as reference utils/geo_utils.mat2quat
+    (:140-207): Shepperd's method -- the quaternion component with the largest magnitude is taken from the diagonal
+    (branch chosen by the signs the reference tests: R22 < eps, R00 > R11, R00 < -R11) and the other three from the
+    off-diagonal sums / differences, so rotations by 180 degrees (trace = -1, w = 0) stay well conditioned."""
     R, t = T[:, :3, :3], T[:, :3, 3]
-    w = torch.sqrt(torch.clamp(1 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2], min=1e-12)) / 2
-    x = (R[:, 2, 1] - R[:, 1, 2]) / (4 * w)
-    y = (R[:, 0, 2] - R[:, 2, 0]) / (4 * w)
-    z = (R[:, 1, 0] - R[:, 0, 1]) / (4 * w)
-    return torch.cat([torch.stack([w, x, y, z], dim=1), t], dim=1)
+    r00, r11, r22 = R[:, 0, 0], R[:, 1, 1], R[:, 2, 2]
+    # antisymmetric parts carry w * (x, y, z); symmetric parts carry the products xy, xz, yz
+    ax, ay, az = R[:, 2, 1] - R[:, 1, 2], R[:, 0, 2] - R[:, 2, 0], R[:, 1, 0] - R[:, 0, 1]
+    sxy, sxz, syz = R[:, 1, 0] + R[:, 0, 1], R[:, 0, 2] + R[:, 2, 0], R[:, 2, 1] + R[:, 1, 2]
+    cand = torch.stack([
+        torch.stack([ax, 1 + r00 - r11 - r22, sxy, sxz], -1),          # x dominant
+        torch.stack([ay, sxy, 1 - r00 + r11 - r22, syz], -1),          # y dominant
+        torch.stack([az, sxz, syz, 1 - r00 - r11 + r22], -1),          # z dominant
+        torch.stack([1 + r00 + r11 + r22, ax, ay, az], -1),            # w dominant
+    ], dim=1)                                                           # [n, 4 branches, 4]
+    low = r22 < eps
+    branch = torch.where(low, torch.where(r00 > r11, 0, 1), torch.where(r00 < -r11, 2, 3))
+    q = cand.gather(1, branch.view(-1, 1, 1).expand(-1, 1, 4)).squeeze(1)
+    diag_pos = torch.where(branch == 3, torch.zeros_like(branch), branch + 1)      # where the branch's "t" sits in q
+    tsel = q.gather(1, diag_pos.view(-1, 1))
+    q = 0.5 * q / torch.sqrt(tsel)
+    return torch.cat([q, t], dim=1)
 
 
 class FORGE(nn.Module):

@@ -70,11 +70,20 @@ class FORGE_poseEstimator3D(nn.Module):
             return camPose_return, 2 * origin_proj / self.config.dataset.img_size
 
         features_transformed = self.rotate(voxels=features_raw, camPoses_cv2=camPoses_cv2[:, :t], grid_size=D)
-        fused = torch.cat([self.encoder_3d.fuse(features_transformed[:, :3]),          # 3-view volume
-                           self.encoder_3d.fuse(features_transformed[:, -2:]),         # 2-view volume
-                           self.encoder_3d.fuse(features_transformed)], dim=0)         # all-view volume  [3b,...]
-        densities = self.encoder_3d.get_density3D(fused)
-        features = self.encoder_3d.get_render_features(fused)
+        f_3v = self.encoder_3d.fuse(features_transformed[:, :3])           # 3-view volume
+        f_2v = self.encoder_3d.fuse(features_transformed[:, -2:])          # 2-view volume
+        f_mv = self.encoder_3d.fuse(features_transformed)                  # all-view volume
+        if self.encoder_3d.density_head.training or self.encoder_3d.features_head.training:
+            # batch-statistics BN: the reference runs the heads on the 2b partial-view volumes and on the b all-view
+            # volumes in separate calls (reference :110-111, :123-124) -- same statistics, same running-stat updates
+            part = torch.cat([f_3v, f_2v], dim=0)
+            densities = torch.cat([self.encoder_3d.get_density3D(part), self.encoder_3d.get_density3D(f_mv)], dim=0)
+            features = torch.cat([self.encoder_3d.get_render_features(part),
+                                  self.encoder_3d.get_render_features(f_mv)], dim=0)
+        else:                                                              # eval-mode BN is per-sample: one 3b call
+            fused = torch.cat([f_3v, f_2v, f_mv], dim=0)
+            densities = self.encoder_3d.get_density3D(fused)
+            features = self.encoder_3d.get_render_features(fused)
         if self.config.dataset.name == 'omniobject3d':
             densities = densities.clamp(min=0.0, max=1.0)
 

@@ -257,10 +257,12 @@ def pack_decoder_bwd_weights(conv_rgb):
 
 
 def _decoder_backward(ctx, g):
-    """Shared backward of the fused decoders.  Constant decoder weights (pose refinement): one kernel from the sign
-    masks the forward pass saved.  Trainable weights: re-run the module's own convs under autograd (cuDNN)."""
+    """Shared backward of the fused decoders -> (grad_x, [grad of every trainable conv_rgb parameter]).  Constant decoder
+    weights (pose refinement): one kernel from the sign masks the forward pass saved.  Trainable weights: re-run the
+    module's own convs under autograd (cuDNN); the parameters are inputs of the Function, so their gradients are
+    returned to autograd (accumulate-grad / DDP hooks fire, torch.autograd.grad has no side effects)."""
     x_nhwc, masks = ctx.saved_tensors
-    params = [p for p in ctx.conv_rgb.parameters() if p.requires_grad]
+    params = ctx.params
     if not params and masks.numel():
         N, Sh, Sw, _ = x_nhwc.shape
         g = _f32c(g)
@@ -268,16 +270,18 @@ def _decoder_backward(ctx, g):
         wb = pack_decoder_bwd_weights(ctx.conv_rgb) if ctx.bwd_pack is None else ctx.bwd_pack
         with torch.cuda.device(g.device):
             _lib.call("forge_decoder_bwd_data", _ptr(g), _ptr(masks), _ptr(wb), _ptr(gx), N, Sh, Sw, _stream(g))
-        return gx
+        return gx, []
     with torch.enable_grad():
-        xi = x_nhwc.detach().requires_grad_(True)
+        xi = x_nhwc.detach().requires_grad_(ctx.needs_input_grad[0])
         y = torch.relu(ctx.conv_rgb(xi.permute(0, 3, 1, 2)))
-        grads = torch.autograd.grad(y, [xi] + params, g, allow_unused=True)
-    for p, gp in zip(params, grads[1:]):        # weights are not Function inputs: accumulate like autograd would
-        if gp is not None:
-            gp = gp.contiguous()
-            p.grad = gp if p.grad is None else p.grad + gp
-    return grads[0]
+        wanted = ([xi] if ctx.needs_input_grad[0] else []) + list(params)
+        grads = list(torch.autograd.grad(y, wanted, g, allow_unused=True)) if wanted else []
+    gx = grads.pop(0) if ctx.needs_input_grad[0] else None
+    return gx, grads
+
+
+def _trainable(conv_rgb):
+    return [p for p in conv_rgb.parameters() if p.requires_grad] if torch.is_grad_enabled() else []
 
 
 def _decoder_masks(ctx, x_nhwc, conv_rgb):
@@ -288,23 +292,25 @@ def _decoder_masks(ctx, x_nhwc, conv_rgb):
 
 
 class _Decoder(torch.autograd.Function):
-    """Fused fp32 inference decoder (see _decoder_backward for the backward pass)."""
+    """Fused fp32 inference decoder (see _decoder_backward for the backward pass); the trainable conv_rgb parameters
+    ride along as inputs so that autograd owns their gradients."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, wpack, conv_rgb, bwd_pack):
+    def forward(ctx, x_nhwc, wpack, conv_rgb, bwd_pack, *params):
         N, Sh, Sw, _ = x_nhwc.shape
         rgb = torch.empty(N, 3, 2 * Sh, 2 * Sw, dtype=torch.float32, device=x_nhwc.device)
         masks = _decoder_masks(ctx, x_nhwc, conv_rgb)
         with torch.cuda.device(x_nhwc.device):
             _lib.call("forge_decoder_fwd", _ptr(x_nhwc), _ptr(wpack), _ptr(rgb), _ptr(masks) if masks.numel() else None,
                       N, Sh, Sw, _stream(x_nhwc))
-        ctx.conv_rgb, ctx.bwd_pack = conv_rgb, bwd_pack
+        ctx.conv_rgb, ctx.bwd_pack, ctx.params = conv_rgb, bwd_pack, params
         ctx.save_for_backward(x_nhwc, masks)
         return rgb
 
     @staticmethod
     def backward(ctx, g):
-        return _decoder_backward(ctx, g), None, None, None
+        gx, gp = _decoder_backward(ctx, g)
+        return (gx, None, None, None, *gp)
 
 
 def decoder_fused(x_nhwc, wpack, conv_rgb, bwd_pack=None):
@@ -313,7 +319,7 @@ def decoder_fused(x_nhwc, wpack, conv_rgb, bwd_pack=None):
     _require_cuda(x_nhwc, wpack)
     if x_nhwc.shape[-1] != 16:
         raise ValueError("the decoder input must have 16 channels")
-    return _Decoder.apply(_f32c(x_nhwc), wpack, conv_rgb, bwd_pack)
+    return _Decoder.apply(_f32c(x_nhwc), wpack, conv_rgb, bwd_pack, *_trainable(conv_rgb))
 
 
 # ---- tensor-core (bf16) decoder ------------------------------------------------------------------
@@ -374,20 +380,21 @@ class _DecoderTC(torch.autograd.Function):
     """bf16 tensor-core inference decoder (see _decoder_backward for the backward pass)."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, wpack, conv_rgb, max_ctas, bwd_pack):
+    def forward(ctx, x_nhwc, wpack, conv_rgb, max_ctas, bwd_pack, *params):
         N, Sh, Sw, _ = x_nhwc.shape
         rgb = torch.empty(N, 3, 2 * Sh, 2 * Sw, dtype=torch.float32, device=x_nhwc.device)
         masks = _decoder_masks(ctx, x_nhwc, conv_rgb)
         with torch.cuda.device(x_nhwc.device):
             _lib.call("forge_decoder_tc_fwd", _ptr(x_nhwc), _ptr(wpack), _ptr(rgb), _ptr(masks) if masks.numel() else None,
                       N, Sh, Sw, int(max_ctas), _stream(x_nhwc))
-        ctx.conv_rgb, ctx.bwd_pack = conv_rgb, bwd_pack
+        ctx.conv_rgb, ctx.bwd_pack, ctx.params = conv_rgb, bwd_pack, params
         ctx.save_for_backward(x_nhwc, masks)
         return rgb
 
     @staticmethod
     def backward(ctx, g):
-        return _decoder_backward(ctx, g), None, None, None, None
+        gx, gp = _decoder_backward(ctx, g)
+        return (gx, None, None, None, None, *gp)
 
 
 def decoder_tc(x_nhwc, wpack, conv_rgb, max_ctas=0, bwd_pack=None):
@@ -396,7 +403,7 @@ def decoder_tc(x_nhwc, wpack, conv_rgb, max_ctas=0, bwd_pack=None):
     _require_cuda(x_nhwc, wpack)
     if x_nhwc.shape[-1] != 16:
         raise ValueError("the decoder input must have 16 channels")
-    return _DecoderTC.apply(_f32c(x_nhwc), wpack, conv_rgb, max_ctas, bwd_pack)
+    return _DecoderTC.apply(_f32c(x_nhwc), wpack, conv_rgb, max_ctas, bwd_pack, *_trainable(conv_rgb))
 
 
 def umma_probe(image_u8, a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo):
