@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
                 return LIB
             tmp = "%s.tmp.%d" % (LIB, os.getpid())
             cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
-                   "-Xptxas", "-v" if verbose else "-O3", "-o", tmp, *_sources()]
+                   "-Xptxas", "-v" if verbose else "-O3", "-o", tmp, *_sources(), "-ldl"]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or res.returncode != 0:
                 sys.stderr.write(res.stdout + res.stderr)

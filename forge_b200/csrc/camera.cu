@@ -195,6 +195,7 @@ __global__ void pose_affine_fwd_kernel(const float* __restrict__ poses, int B, i
 
 extern "C" int forge_camera_prep_fwd(const float* R, const float* T, const float* K_half, int N, float sx, float sy, float sz,
                                      float eps, float* cam12, float* origin_proj, void* stream) {
+    FORGE_RANGE("forge_camera_prep_fwd");
     using namespace forge;
     const char* fn = "forge_camera_prep_fwd";
     if (!R || !T || !K_half || !cam12) return fail(fn, "null pointer");
@@ -208,6 +209,7 @@ extern "C" int forge_camera_prep_fwd(const float* R, const float* T, const float
 extern "C" int forge_camera_prep_bwd(const float* R, const float* T, const float* K_half, int N, float sx, float sy, float sz,
                                      float eps, const float* g_cam12, const float* g_origin_proj, float* grad_R, float* grad_T,
                                      float* grad_K, void* stream) {
+    FORGE_RANGE("forge_camera_prep_bwd");
     using namespace forge;
     const char* fn = "forge_camera_prep_bwd";
     if (!R || !T || !K_half) return fail(fn, "null pointer");
@@ -219,6 +221,7 @@ extern "C" int forge_camera_prep_bwd(const float* R, const float* T, const float
 
 extern "C" int forge_pose_affine_fwd(const float* poses, int B, int t, float* affine12, float* pose_inv, int* singular_flag,
                                      void* stream) {
+    FORGE_RANGE("forge_pose_affine_fwd");
     using namespace forge;
     const char* fn = "forge_pose_affine_fwd";
     if (!poses || !affine12) return fail(fn, "null pointer");
@@ -306,6 +309,7 @@ upsample2x_bwd_kernel(const float* __restrict__ g0, const float* __restrict__ g1
 
 extern "C" int forge_upsample2x_fwd(const float* src0, const float* src1, float* dst0, float* dst1, int M, int S_h, int S_w,
                                     void* stream) {
+    FORGE_RANGE("forge_upsample2x_fwd");
     using namespace forge;
     const char* fn = "forge_upsample2x_fwd";
     if (!src0 || !dst0 || (src1 && !dst1)) return fail(fn, "null pointer");
@@ -320,6 +324,7 @@ extern "C" int forge_upsample2x_fwd(const float* src0, const float* src1, float*
 
 extern "C" int forge_upsample2x_bwd(const float* g_dst0, const float* g_dst1, float* g_src0, float* g_src1, int M, int S_h,
                                     int S_w, void* stream) {
+    FORGE_RANGE("forge_upsample2x_bwd");
     using namespace forge;
     const char* fn = "forge_upsample2x_bwd";
     if (!g_dst0 || !g_src0 || (g_dst1 && !g_src1)) return fail(fn, "null pointer");

@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/forge_b200.h"
 
 namespace forge {
@@ -17,6 +19,14 @@ int check_launch(const char* fn);
 int ensure_dynamic_smem(const char* fn, const void* kernel, size_t bytes);
 // Multiprocessor count of the current device (cached per device); 0 + error string on failure.
 int current_sm_count(const char* fn);
+
+// NVTX range around every C-ABI entry point (SURVEY 5 "Tracing"): header-only NVTX v3, a no-op pointer check unless a
+// tool (nsys / ncu --nvtx) is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define FORGE_RANGE(name) ::forge::NvtxRange forge_nvtx_range_(name)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -295,6 +295,7 @@ extern "C" int forge_decoder_wpack_floats(void) { return forge::WPACK_N; }
 
 extern "C" int forge_decoder_fwd(const float* x_nhwc, const float* wpack, float* rgb_nchw, unsigned* sign_masks, int N,
                                  int S_h, int S_w, void* stream) {
+    FORGE_RANGE("forge_decoder_fwd");
     using namespace forge;
     const char* fn = "forge_decoder_fwd";
     if (!x_nhwc || !wpack || !rgb_nchw) return fail(fn, "null pointer");

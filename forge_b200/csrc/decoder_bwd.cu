@@ -272,6 +272,7 @@ extern "C" int forge_decoder_bwd_wpack_floats(void) { return forge::dbw::WPACK_N
 
 extern "C" int forge_decoder_bwd_data(const float* g_rgb_nchw, const unsigned* masks, const float* wpack_bwd, float* g_x_nhwc,
                                       int N, int S_h, int S_w, void* stream) {
+    FORGE_RANGE("forge_decoder_bwd_data");
     using namespace forge;
     using namespace forge::dbw;
     const char* fn = "forge_decoder_bwd_data";

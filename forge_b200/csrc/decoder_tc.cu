@@ -479,6 +479,7 @@ extern "C" int forge_decoder_tc_wpack_bytes(void) { return forge::dtc::WPACK_BYT
 
 extern "C" int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, float* rgb_nchw, unsigned* sign_masks, int N,
                                     int S_h, int S_w, int max_ctas, void* stream) {
+    FORGE_RANGE("forge_decoder_tc_fwd");
     using namespace forge;
     using namespace forge::dtc;
     const char* fn = "forge_decoder_tc_fwd";
@@ -502,6 +503,7 @@ extern "C" int forge_decoder_tc_fwd(const float* x_nhwc, const void* wpack, floa
 
 extern "C" int forge_umma_probe(const void* image, int image_bytes, unsigned a_off, unsigned a_lbo, unsigned a_sbo,
                                 unsigned b_off, unsigned b_lbo, unsigned b_sbo, float* out, void* stream) {
+    FORGE_RANGE("forge_umma_probe");
     using namespace forge;
     using namespace forge::dtc;
     const char* fn = "forge_umma_probe";

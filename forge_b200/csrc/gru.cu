@@ -214,6 +214,7 @@ inline int vec_width(int cl, int C, int S, long long h_bs, long long x_bs, std::
 
 extern "C" int forge_gru_gate_fwd(const void* g, int g_bf16, const float* h, long long h_bs, const float* x, long long x_bs,
                                   float* xhr, int channels_last, int B, int C, int S, void* stream) {
+    FORGE_RANGE("forge_gru_gate_fwd");
     using namespace forge;
     using namespace forge::gru;
     const char* fn = "forge_gru_gate_fwd";
@@ -227,6 +228,7 @@ extern "C" int forge_gru_gate_fwd(const void* g, int g_bf16, const float* h, lon
 
 extern "C" int forge_gru_gate_bwd(const float* d_xhr, const void* g, int g_bf16, const float* h, long long h_bs, void* d_g,
                                   float* d_h, float* d_x, int channels_last, int B, int C, int S, void* stream) {
+    FORGE_RANGE("forge_gru_gate_bwd");
     using namespace forge;
     using namespace forge::gru;
     const char* fn = "forge_gru_gate_bwd";
@@ -241,6 +243,7 @@ extern "C" int forge_gru_gate_bwd(const float* d_xhr, const void* g, int g_bf16,
 
 extern "C" int forge_gru_out_fwd(const void* o, const void* g, int og_bf16, const float* h, long long h_bs, float* h_new,
                                  int channels_last, int B, int C, int S, void* stream) {
+    FORGE_RANGE("forge_gru_out_fwd");
     using namespace forge;
     using namespace forge::gru;
     const char* fn = "forge_gru_out_fwd";
@@ -255,6 +258,7 @@ extern "C" int forge_gru_out_fwd(const void* o, const void* g, int og_bf16, cons
 
 extern "C" int forge_gru_out_bwd(const float* d_h_new, const void* o, const void* g, int og_bf16, const float* h, long long h_bs,
                                  void* d_o, void* d_g, float* d_h, int channels_last, int B, int C, int S, void* stream) {
+    FORGE_RANGE("forge_gru_out_bwd");
     using namespace forge;
     using namespace forge::gru;
     const char* fn = "forge_gru_out_bwd";

@@ -301,6 +301,7 @@ int forge_sample_points(const float* pts, int M, int D, int H, int W, int align_
 
 extern "C" int forge_pack_volume(const float* feat, int feat_channels_last, const float* dens, float* feat_pad,
                                  float* dens_quad, int V, int D, int H, int W, void* stream) {
+    FORGE_RANGE("forge_pack_volume");
     using namespace forge;
     const char* fn = "forge_pack_volume";
     if (!feat || !dens || !feat_pad || !dens_quad) return fail(fn, "null pointer");
@@ -320,6 +321,7 @@ extern "C" int forge_pack_volume(const float* feat, int feat_channels_last, cons
 
 extern "C" int forge_unpack_volume_grad(const float* grad_feat_pad, float* grad_feat, int channels_last, int V, int D,
                                         int H, int W, void* stream) {
+    FORGE_RANGE("forge_unpack_volume_grad");
     using namespace forge;
     const char* fn = "forge_unpack_volume_grad";
     if (!grad_feat_pad || !grad_feat) return fail(fn, "null pointer");

@@ -461,6 +461,7 @@ extern "C" int forge_raymarch_fwd(const float* feat_pad, const float* dens_quad,
                                   const float* cam12, const float* zs, float* out_feat, float* out_sil,
                                   float* out_depth, int N, int V, int D, int H, int W, int S_h, int S_w, int P,
                                   void* stream) {
+    FORGE_RANGE("forge_raymarch_fwd");
     using namespace forge;
     const char* fn = "forge_raymarch_fwd";
     if (!feat_pad || !dens_quad || !view2vol || !cam12 || !zs || !out_feat || !out_sil) return fail(fn, "null pointer");
@@ -517,6 +518,7 @@ extern "C" int forge_raymarch_bwd(const float* feat_pad, const float* dens_quad,
                                   const float* g_depth, float* grad_feat_pad, float* grad_dens_pad, float* grad_cam12,
                                   float* workspace, int N, int V, int D, int H, int W, int S_h, int S_w, int P,
                                   void* stream) {
+    FORGE_RANGE("forge_raymarch_bwd");
     using namespace forge;
     const char* fn = "forge_raymarch_bwd";
     if (!feat_pad || !dens_quad || !view2vol || !cam12 || !zs || !g_feat || !g_sil) return fail(fn, "null pointer");

@@ -295,6 +295,7 @@ static int rotate_check(const char* fn, const void* vox, const void* aff, const 
 extern "C" int forge_rotate_fwd(const float* vox_cl, const float* affine12, const int* jobs, const float* gx,
                                 const float* gy, const float* gz, float grid_coord_max, float* out_cl, int M, int C,
                                 int D, int H, int W, void* stream) {
+    FORGE_RANGE("forge_rotate_fwd");
     using namespace forge;
     const char* fn = "forge_rotate_fwd";
     if (int e = rotate_check(fn, vox_cl, affine12, jobs, gx, gy, gz, grid_coord_max, M, C, D, H, W)) return e;
@@ -365,6 +366,7 @@ extern "C" int forge_rotate_bwd(const float* vox_cl, const float* affine12, cons
                                 const float* gy, const float* gz, float grid_coord_max, const float* g_out_cl,
                                 float* grad_vox_cl, float* grad_affine12, int M, int C, int D, int H, int W,
                                 void* stream) {
+    FORGE_RANGE("forge_rotate_bwd");
     using namespace forge;
     const char* fn = "forge_rotate_bwd";
     if (int e = rotate_check(fn, vox_cl, affine12, jobs, gx, gy, gz, grid_coord_max, M, C, D, H, W)) return e;
