@@ -22,6 +22,8 @@ _SIGNATURES = {
     "forge_pack_volume": (_c.c_int, [_F, _I, _F, _F, _F, _I, _I, _I, _I, _F]),
     "forge_unpack_volume_grad": (_c.c_int, [_F, _F, _I, _I, _I, _I, _I, _F]),
     "forge_raymarch_fwd": (_c.c_int, [_F] * 8 + [_I] * 8 + [_F]),
+    "forge_raymarch_fwd_gather": (_c.c_int, [_F] * 8 + [_I] * 8 + [_F]),
+    "forge_raymarch_fwd_tma": (_c.c_int, [_F] * 8 + [_I] * 8 + [_F]),
     "forge_raymarch_bwd": (_c.c_int, [_F] * 12 + [_I] * 8 + [_F]),
     "forge_raymarch_bwd_workspace": (_c.c_longlong, [_I] * 4),
     "forge_rotate_fwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F] + [_I] * 5 + [_F]),
@@ -44,7 +46,7 @@ _SIGNATURES = {
     "forge_gru_out_bwd": (_c.c_int, [_F, _F, _F, _I, _F, _c.c_longlong, _F, _F, _F, _I, _I, _I, _I, _F]),
     "forge_sample_points": (_c.c_int, [_F, _I, _I, _I, _I, _I, _F, _F, _F]),
 }
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _lock = threading.Lock()
 _lib = None

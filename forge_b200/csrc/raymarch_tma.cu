@@ -1,0 +1,314 @@
+// K1-T: the raymarch forward with TMA-staged voxel bricks in shared memory (the formulation BASELINE.json's north_star
+// names).  Same inputs, outputs and sampling arithmetic as raymarch_fwd_kernel (raymarch.cu); what changes is the operand
+// path of the 16-channel features:
+//
+//   * a CTA marches a 16x8 pixel tile of one view in k-SLABS (runs of consecutive sample depths).  The samples of a slab
+//     form a frustum segment whose voxel footprint is bounded by the axis-aligned box of its 8 vertices (positions are
+//     multilinear in pixel and depth); a producer warp fetches exactly that box from the packed volume with TMA bulk
+//     copies (one cp.async.bulk per x-row of the box, UBLKCP in SASS) into a 2-stage shared-memory ring behind
+//     full / empty mbarriers.  Slab lengths adapt so that every box fits its stage (<= 832 voxels = 52 KB).
+//   * the 8 consumer warps read corners with LDS.128.  Mapping: 2 lanes per ray, lane c owns the x-corner x0 + c and all
+//     16 channels; the four 16-byte chunks of a voxel are read in an order rotated by the ray's index in its quarter-warp
+//     (chunk = i ^ (ray & 3)), so the 8 lanes of a shared-memory phase always hit 8 distinct 4-bank groups: x0 and x0+1
+//     are adjacent 64-byte records (opposite bank halves) and the four rays use four different chunk slots.  Every
+//     LDS.128 phase is therefore one conflict-free wavefront: 4 wavefronts per ray-sample, the minimum for 512 bytes,
+//     where the direct L1 gathers of raymarch_fwd_kernel need ~6.3 (one per distinct 128-byte line of a request).
+//   * each voxel crosses L2 -> SM about once per slab it is used in (bricks are shared by the 128 rays of the tile), and
+//     nothing is re-fetched through the L1 tag path.
+//
+// A sample whose footprint is not completely inside the resident brick (possible only through rounding at the box faces or
+// a clipped box) takes the direct global path, so results never depend on the box arithmetic.  Density stays on the
+// global path (dens_quad: 32 bytes per sample against 512 for the features).
+#include <cstdlib>
+
+#include "async.cuh"
+#include "raymarch_common.cuh"
+
+namespace forge {
+
+using namespace async_;
+
+constexpr int kTW = 16, kTH = 8;                  // pixel tile of a CTA
+constexpr int kConsWarps = 8;                     // 8 warps x 16 rays x 2 lanes
+constexpr int kTmaThreads = 32 * (kConsWarps + 1);
+constexpr int kStages = 2;
+constexpr int kStageVox = 832;                    // voxels per stage (64 B each)
+constexpr int kSlabMax = 8;                       // most samples per slab
+
+struct SlabHeader {
+    int ka, kb;          // sample range [ka, kb)
+    int lx, ly, lz;      // box origin in padded voxel coordinates
+    int ex, ey, ez;      // box extent (0 = nothing resident)
+};
+
+struct TmaSmem {
+    unsigned long long full[kStages], empty[kStages];
+    SlabHeader hdr[kStages];
+    float cam[12];
+    int kt0, kt1;
+    float zs[kMaxP];
+};
+constexpr int kTmaSmemBytes = kStages * kStageVox * 64 + static_cast<int>(sizeof(TmaSmem));
+
+struct Box {
+    int lo[3], ex[3];
+    __device__ __forceinline__ int vol() const { return ex[0] * ex[1] * ex[2]; }
+};
+
+// Box (padded voxel coordinates, clipped to the padded volume) of all corner footprints of the samples k in [ka, kb) of
+// the tile's rays: positions are multilinear in (pixel, depth), so the 4 corner rays at the 2 end depths bound them.
+__device__ __forceinline__ Box slab_box(const float* cam, const float* zs, int ka, int kb, float u0, float u1, float v0,
+                                        float v1, int D, int H, int W) {
+    const float za = zs[ka], zb = zs[kb - 1];
+    const int size[3] = {W, H, D};
+    Box b;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float m0 = cam[3 + 3 * a], m1 = cam[4 + 3 * a], m2 = cam[5 + 3 * a], o = cam[a];
+        float lo = 3.0e38f, hi = -3.0e38f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float d = fmaf(m0, (c & 1) ? u1 : u0, fmaf(m1, (c & 2) ? v1 : v0, m2));
+            const float pa = fmaf(za, d, o), pb = fmaf(zb, d, o);
+            lo = fminf(lo, fminf(pa, pb));
+            hi = fmaxf(hi, fmaxf(pa, pb));
+        }
+        // padded voxel coordinate = (p + 1) / 2 * (size - 1) + 1; base = floor, upper corner = base + 1
+        const float s = 0.5f * static_cast<float>(size[a] - 1);
+        lo = fmaxf(fminf((lo + 1.f) * s + 1.f - 1e-3f, 3.0e4f), -3.0e4f);
+        hi = fmaxf(fminf((hi + 1.f) * s + 1.f + 1e-3f, 3.0e4f), -3.0e4f);
+        int l = static_cast<int>(floorf(lo)), h = static_cast<int>(floorf(hi)) + 1;
+        l = max(l, 0);
+        h = min(h, size[a] + 1);
+        b.lo[a] = l;
+        b.ex[a] = max(h - l + 1, 0);
+    }
+    if (b.ex[0] == 0 || b.ex[1] == 0 || b.ex[2] == 0) b.ex[0] = b.ex[1] = b.ex[2] = 0;
+    return b;
+}
+
+__device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void fma4(float* acc, float w, const float4 v) {
+    const float2 w2 = make_float2(w, w);
+    float2 a = __ffma2_rn(make_float2(v.x, v.y), w2, make_float2(acc[0], acc[1]));
+    float2 b = __ffma2_rn(make_float2(v.z, v.w), w2, make_float2(acc[2], acc[3]));
+    acc[0] = a.x, acc[1] = a.y, acc[2] = b.x, acc[3] = b.y;
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 2)
+raymarch_fwd_tma_kernel(const float* __restrict__ feat_pad, const float4* __restrict__ dens_quad,
+                        const int* __restrict__ view2vol, const float* __restrict__ cam12, const float* __restrict__ zs_g,
+                        float* __restrict__ out_feat, float* __restrict__ out_sil, float* __restrict__ out_depth, int D,
+                        int H, int W, int Sh, int Sw, int P, int tiles_x, int interleave) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw + kStages * kStageVox * 64);
+    const uint32_t stage0 = smem_u32(smem_raw);
+
+    // heavy-first schedule, as in raymarch_fwd_kernel: views interleaved, tiles ranked centre-out
+    const int order = blockIdx.y * gridDim.x + blockIdx.x, n_views = gridDim.y, tiles_y = gridDim.x / tiles_x;
+    const int rank = interleave ? order / n_views : static_cast<int>(blockIdx.x);
+    const int n = interleave ? order - rank * n_views : static_cast<int>(blockIdx.y);
+    const int ty = centre_out(rank / tiles_x, tiles_y), tx = centre_out(rank % tiles_x, tiles_x);
+
+    for (int k = threadIdx.x; k < P; k += kTmaThreads) sm.zs[k] = zs_g[k];
+    if (threadIdx.x < 12) sm.cam[threadIdx.x] = cam12[n * 12 + threadIdx.x];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], kConsWarps);
+        }
+        sm.kt0 = P;
+        sm.kt1 = 0;
+        mbar_init_fence();
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Wp = W + 2, Hp = H + 2, Wq = W + 1, Hq = H + 1;
+    const long long v = view2vol[n];
+    const float* fvol = feat_pad + v * (D + 2) * Hp * Wp * 16;
+
+    // ---- per-ray setup (consumer warps) and the tile's sample range ----
+    const int c = lane & 1, q = lane >> 1, rq = q & 3;
+    const int j = tx * kTW + (warp & 3) * 4 + (q & 3);
+    const int i = ty * kTH + ((warp >> 2) & 1) * 4 + (q >> 2);
+    const bool valid = (warp < kConsWarps) && (i < Sh) && (j < Sw);
+    Ray r;
+    r.k0 = 0;
+    r.k1 = 0;
+    if (warp < kConsWarps) {
+        r = make_ray(sm.cam, i, j, sm.zs, P, D, H, W);
+        if (!valid) r.k1 = 0;
+    }
+    int kw0 = r.k1 > r.k0 ? r.k0 : P, kw1 = r.k1 > r.k0 ? r.k1 : 0;
+#pragma unroll
+    for (int s = 16; s >= 2; s >>= 1) {
+        kw0 = min(kw0, __shfl_xor_sync(0xffffffffu, kw0, s));
+        kw1 = max(kw1, __shfl_xor_sync(0xffffffffu, kw1, s));
+    }
+    if (lane == 0 && warp < kConsWarps && kw1 > kw0) {
+        atomicMin(&sm.kt0, kw0);
+        atomicMax(&sm.kt1, kw1);
+    }
+    __syncthreads();
+    const int kt0 = sm.kt0, kt1 = sm.kt1;
+    if (kt1 <= kt0) {          // the whole tile misses the volume
+        if (valid) {
+            const long long pix = (static_cast<long long>(n) * Sh + i) * Sw + j;
+            float4* o = reinterpret_cast<float4*>(out_feat + pix * 16 + c * 8);
+            o[0] = o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c == 0) {
+                out_sil[pix] = 0.f;
+                if (out_depth) out_depth[pix] = 0.f;
+            }
+        }
+        return;
+    }
+
+    if (warp == kConsWarps) {
+        // ================= producer warp: slab schedule + TMA bulk copies =================
+        const float u0 = static_cast<float>(tx * kTW) + 0.5f, u1 = static_cast<float>(min(tx * kTW + kTW, Sw) - 1) + 0.5f;
+        const float v0 = static_cast<float>(ty * kTH) + 0.5f, v1 = static_cast<float>(min(ty * kTH + kTH, Sh) - 1) + 0.5f;
+        int ka = kt0;
+        for (int it = 0; ka < kt1; ++it) {
+            const int st = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&sm.empty[st], ph ^ 1);
+            // greedy slab: extend while the box fits the stage (every lane computes the same thing: no broadcast needed)
+            int kb = ka + 1;
+            Box box = slab_box(sm.cam, sm.zs, ka, kb, u0, u1, v0, v1, D, H, W);
+            while (kb < kt1 && kb - ka < kSlabMax) {
+                const Box nb = slab_box(sm.cam, sm.zs, ka, kb + 1, u0, u1, v0, v1, D, H, W);
+                if (nb.vol() > kStageVox) break;
+                box = nb;
+                ++kb;
+            }
+            while (box.vol() > kStageVox) --box.ex[2];        // a single sample that does not fit: clip (the rest gathers directly)
+            const int rows = box.ex[1] * box.ex[2];
+            const uint32_t row_bytes = static_cast<uint32_t>(box.ex[0]) * 64u;
+            if (lane == 0) {
+                SlabHeader h;
+                h.ka = ka, h.kb = kb;
+                h.lx = box.lo[0], h.ly = box.lo[1], h.lz = box.lo[2];
+                h.ex = box.ex[0], h.ey = box.ex[1], h.ez = box.ex[2];
+                sm.hdr[st] = h;
+                if (rows > 0) mbar_arrive_expect_tx(&sm.full[st], row_bytes * static_cast<uint32_t>(rows));
+                else mbar_arrive(&sm.full[st]);
+            }
+            __syncwarp();
+            const uint32_t dst0 = stage0 + static_cast<uint32_t>(st) * (kStageVox * 64);
+            for (int rw = lane; rw < rows; rw += 32) {
+                const int zz = rw / box.ex[1], yy = rw - zz * box.ex[1];
+                const float* src = fvol + ((static_cast<long long>(box.lo[2] + zz) * Hp + (box.lo[1] + yy)) * Wp + box.lo[0]) * 16;
+                bulk_g2s(dst0 + static_cast<uint32_t>(rw) * row_bytes, src, row_bytes, &sm.full[st]);
+            }
+            ka = kb;
+        }
+        return;
+    }
+
+    // ================= consumer warps =================
+    const float4* qv = dens_quad + v * (D + 2) * Hq * Wq;
+    const int row_y = Wp * 16, row_z = Hp * Wp * 16;          // float strides of the padded feature volume
+    uint32_t choff[4];                                        // byte offset of the chunk this lane reads i-th
+#pragma unroll
+    for (int e = 0; e < 4; ++e) choff[e] = static_cast<uint32_t>((e ^ rq) << 4);
+
+    float acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    float T = 1.f, depth = 0.f;
+
+    int k = kt0;
+    for (int it = 0; k < kt1; ++it) {
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&sm.full[st], ph);
+        const SlabHeader h = sm.hdr[st];
+        const uint32_t brick = stage0 + static_cast<uint32_t>(st) * (kStageVox * 64);
+        const int kend = min(h.kb, kw1);
+        for (k = max(h.ka, kw0); k < kend; ++k) {
+            const float z = sm.zs[k];
+            const Foot f = sample_foot(r, z, D, H, W);
+            const bool act = f.in && (k >= r.k0) && (k < r.k1);
+            const float w00 = __fmul_rn(f.wx0, f.wy0), w10 = __fmul_rn(f.wx1, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1),
+                        w11 = __fmul_rn(f.wx1, f.wy1);
+            float part = 0.f;
+            if (act) {          // density: lane c owns plane z0 + c (one 16-byte quad = its four x/y corners)
+                const float wz = c ? f.wz1 : f.wz0;
+                const float4 d4 = __ldg(qv + (static_cast<long long>(f.z0 + 1 + c) * Hq + (f.y0 + 1)) * Wq + (f.x0 + 1));
+                part = __fmul_rn(w00, wz) * d4.x;
+                part = fmaf(__fmul_rn(w10, wz), d4.y, part);
+                part = fmaf(__fmul_rn(w01, wz), d4.z, part);
+                part = fmaf(__fmul_rn(w11, wz), d4.w, part);
+            }
+            const float sigma = part + __shfl_xor_sync(0xffffffffu, part, 1);
+            const float wk = sigma * T;
+            if (wk != 0.f) {    // sigma != 0 implies act
+                // features: lane c owns the x-corner x0 + c; weights in ATen's order (wx wy) wz, times the sample weight
+                const float wy0 = c ? w10 : w00, wy1 = c ? w11 : w01;
+                const float cw[4] = {wk * __fmul_rn(wy0, f.wz0), wk * __fmul_rn(wy1, f.wz0), wk * __fmul_rn(wy0, f.wz1),
+                                     wk * __fmul_rn(wy1, f.wz1)};        // index = dz * 2 + dy
+                const int xb = f.x0 + 1 - h.lx, yb = f.y0 + 1 - h.ly, zb = f.z0 + 1 - h.lz;
+                const bool inbox = (static_cast<unsigned>(xb) + 1u < static_cast<unsigned>(h.ex)) &&
+                                   (static_cast<unsigned>(yb) + 1u < static_cast<unsigned>(h.ey)) &&
+                                   (static_cast<unsigned>(zb) + 1u < static_cast<unsigned>(h.ez));
+                if (inbox) {
+                    const uint32_t a0 = brick + static_cast<uint32_t>(((zb * h.ey + yb) * h.ex + xb + c) << 6);
+                    const uint32_t sy = static_cast<uint32_t>(h.ex) << 6, sz = static_cast<uint32_t>(h.ex * h.ey) << 6;
+#pragma unroll
+                    for (int cn = 0; cn < 4; ++cn) {
+                        const uint32_t a = a0 + ((cn & 2) ? sz : 0u) + ((cn & 1) ? sy : 0u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) fma4(acc + 4 * e, cw[cn], lds128(a + choff[e]));
+                    }
+                } else {
+                    const float* p = fvol + ((f.z0 + 1) * Hp + (f.y0 + 1)) * row_y + (f.x0 + 1 + c) * 16;
+#pragma unroll
+                    for (int cn = 0; cn < 4; ++cn) {
+                        const float* pc = p + ((cn & 2) ? row_z : 0) + ((cn & 1) ? row_y : 0);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) fma4(acc + 4 * e, cw[cn], ldg128(pc + (choff[e] >> 2)));
+                    }
+                }
+                depth = fmaf(wk, z, depth);
+            }
+            T = T * (1.f - sigma);
+        }
+        k = h.kb;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);
+    }
+
+    // ---- combine the two x-corner halves of the pair, store (acc[4 e + t] is channel 4 (e ^ rq) + t) ----
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
+    if (valid) {
+        const long long pix = (static_cast<long long>(n) * Sh + i) * Sw + j;
+        float* o = out_feat + pix * 16;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if ((e >> 1) == c)
+                *reinterpret_cast<float4*>(o + (choff[e] >> 2)) = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+        if (c == 0) {
+            out_sil[pix] = 1.f - T;
+            if (out_depth) out_depth[pix] = depth;
+        }
+    }
+}
+
+int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4* dens_quad, const int* view2vol,
+                            const float* cam12, const float* zs, float* out_feat, float* out_sil, float* out_depth, int N,
+                            int V, int D, int H, int W, int S_h, int S_w, int P, cudaStream_t st) {
+    if (int e = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(raymarch_fwd_tma_kernel), kTmaSmemBytes)) return e;
+    const int tiles_x = (S_w + kTW - 1) / kTW, tiles_y = (S_h + kTH - 1) / kTH;
+    dim3 grid(tiles_x * tiles_y, N);
+    raymarch_fwd_tma_kernel<<<grid, kTmaThreads, kTmaSmemBytes, st>>>(feat_pad, dens_quad, view2vol, cam12, zs, out_feat,
+                                                                       out_sil, out_depth, D, H, W, S_h, S_w, P, tiles_x,
+                                                                       interleave_views(V, D, H, W));
+    return check_launch(fn);
+}
+
+}  // namespace forge

@@ -6,6 +6,7 @@ a 64 x 32^3 volume, one Conv3d to 128 channels; ``features_head`` (128 -> 16 ch,
 Same child / parameter names as the reference, so its checkpoints load with ``strict=True``.
 All of this stays PyTorch/cuDNN (SURVEY 8a rows a11-a13 are host rows).
 """
+import os
 import warnings
 
 import torch
@@ -82,10 +83,17 @@ class Encoder3D(nn.Module):
 def get_resnet50():
     """ImageNet ResNet-50 without avgpool/fc, layer3/layer4 strides set to 1 (reference :71-78).
     Offline (no weight download possible) the trunk is randomly initialised, with a warning."""
-    try:
-        model = torchvision.models.resnet50(weights=torchvision.models.ResNet50_Weights.IMAGENET1K_V1)
-    except Exception as e:   # no network / no cached weights
-        warnings.warn("ImageNet weights for ResNet-50 unavailable (%s); using random init" % type(e).__name__)
+    weights = torchvision.models.ResNet50_Weights.IMAGENET1K_V1
+    cached = os.path.join(torch.hub.get_dir(), 'checkpoints', os.path.basename(weights.url))
+    if os.path.exists(cached) or os.environ.get('FORGE_ALLOW_DOWNLOAD') == '1':
+        try:
+            model = torchvision.models.resnet50(weights=weights)
+        except Exception as e:   # no network / corrupt cache
+            warnings.warn("ImageNet weights for ResNet-50 unavailable (%s); using random init" % type(e).__name__)
+            model = torchvision.models.resnet50(weights=None)
+    else:    # never touch the network implicitly (the reference downloads at construction time, models/encoder.py:72)
+        warnings.warn("ImageNet weights for ResNet-50 are not in the torch hub cache (%s); using random init "
+                      "(set FORGE_ALLOW_DOWNLOAD=1 to fetch them)" % cached)
         model = torchvision.models.resnet50(weights=None)
     feature = nn.Sequential(*list(model.children())[:-2])
     for stage in (6, 7):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 12
+#define FORGE_ABI_VERSION 13
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -65,6 +65,20 @@ int forge_raymarch_fwd(const float* feat_pad, const float* dens_quad, const int*
                        const float* cam12, const float* zs, float* out_feat, float* out_sil,
                        float* out_depth, int N, int V, int D, int H, int W, int S_h, int S_w, int P,
                        void* stream);
+
+/* The two formulations of the forward kernel behind forge_raymarch_fwd, callable directly (same arguments, same
+ * results to fp32 summation order): `_gather` = direct 256-bit L1 gathers of the 8 corners (raymarch.cu),
+ * `_tma` = voxel bricks of a 16x8 pixel tile x k-slab staged in shared memory by TMA bulk copies behind an
+ * mbarrier ring, corners read with conflict-free LDS.128 (raymarch_tma.cu).  forge_raymarch_fwd picks one
+ * (environment override FORGE_K1_IMPL=gather|tma, read once). */
+int forge_raymarch_fwd_gather(const float* feat_pad, const float* dens_quad, const int* view2vol,
+                              const float* cam12, const float* zs, float* out_feat, float* out_sil,
+                              float* out_depth, int N, int V, int D, int H, int W, int S_h, int S_w, int P,
+                              void* stream);
+int forge_raymarch_fwd_tma(const float* feat_pad, const float* dens_quad, const int* view2vol,
+                           const float* cam12, const float* zs, float* out_feat, float* out_sil,
+                           float* out_depth, int N, int V, int D, int H, int W, int S_h, int S_w, int P,
+                           void* stream);
 
 /* Backward of forge_raymarch_fwd on the same packed inputs.  g_* are the upstream gradients
  * (g_depth may be NULL).  grad_feat_pad (feat_pad layout) and grad_dens_pad [V][D+2][H+2][W+2]

@@ -89,8 +89,8 @@ def main():
     o_sil = torch.empty(N, S, S, device=DEV)
     o_dep = torch.empty(N, S, S, device=DEV)
 
-    def k1():
-        _lib.call("forge_raymarch_fwd", fp.data_ptr(), dq.data_ptr(), inp['view2vol'].data_ptr(), cam12.data_ptr(),
+    def k1(entry="forge_raymarch_fwd"):
+        _lib.call(entry, fp.data_ptr(), dq.data_ptr(), inp['view2vol'].data_ptr(), cam12.data_ptr(),
                   zs.data_ptr(), o_feat.data_ptr(), o_sil.data_ptr(), o_dep.data_ptr(), N, b, D, D, D, S, S, P,
                   torch.cuda.current_stream().cuda_stream)
 
@@ -104,6 +104,11 @@ def main():
             ms, best = timeit(k1, args.reps, flush)
             report("raymarch_fwd", ms, best, k1_bytes, Mrays_per_s=round(rays / ms / 1e3, 1),
                    fp32_TFLOPs=round(rays * P * 366 / ms / 1e9, 2))
+        if want("k1ab"):       # the two forward formulations side by side
+            k1_bytes = b * 17 * D ** 3 * 4 + rays * 18 * 4 + N * 48
+            for entry in ("forge_raymarch_fwd_gather", "forge_raymarch_fwd_tma"):
+                ms, best = timeit(lambda: k1(entry), args.reps, flush)
+                report(entry, ms, best, k1_bytes, Mrays_per_s=round(rays / ms / 1e3, 1))
         if want("volrender"):
             def full():
                 cam = dict(R=inp['R'], T=inp['T'], K=inp['K'].clone())
