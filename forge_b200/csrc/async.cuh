@@ -18,11 +18,13 @@ __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     uint32_t done = 0;
     for (int spins = 0; !done; ++spins) {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        // suspend-time hint (ns): the warp sleeps in hardware until the phase completes or the hint expires, instead of
+        // re-issuing the probe every few hundred cycles (ncu: a quarter of all issued instructions were probe re-issues)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done)
-                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
                      : "memory");
-        if (spins > (1 << 22)) __trap();
+        if (spins > (1 << 20)) __trap();
     }
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {

@@ -2,7 +2,7 @@
 #include <mutex>
 #include <vector>
 
-#include "common.cuh"
+#include "tensormap.cuh"
 
 namespace forge {
 
@@ -72,6 +72,36 @@ int current_sm_count(const char* fn) {
         g_sm_count[dev] = n;
     }
     return g_sm_count[dev];
+}
+
+int encode_tensor_map(const char* fn, CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base,
+                      const unsigned long long* dims, const unsigned long long* strides_bytes, const unsigned* box,
+                      CUtensorMapSwizzle swizzle) {
+    using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode encode = [] {       // resolved once through the runtime (no link against libcuda)
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &st) != cudaSuccess ||
+            st != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<Encode>(f);
+    }();
+    if (!encode) return fail(fn, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gd[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) gs[i - 1] = strides_bytes[i - 1];
+    }
+    const CUresult r = encode(out, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gd, gs, bx, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(fn, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 0;
 }
 
 // ---- transposes ---------------------------------------------------------------------------------

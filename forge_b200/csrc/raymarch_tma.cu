@@ -2,53 +2,65 @@
 // names).  Same inputs, outputs and sampling arithmetic as raymarch_fwd_kernel (raymarch.cu); what changes is the operand
 // path of the 16-channel features:
 //
-//   * a CTA marches a 16x8 pixel tile of one view in k-SLABS (runs of consecutive sample depths).  The samples of a slab
-//     form a frustum segment whose voxel footprint is bounded by the axis-aligned box of its 8 vertices (positions are
-//     multilinear in pixel and depth); a producer warp fetches exactly that box from the packed volume with TMA bulk
-//     copies (one cp.async.bulk per x-row of the box, UBLKCP in SASS) into a 2-stage shared-memory ring behind
-//     full / empty mbarriers.  Slab lengths adapt so that every box fits its stage (<= 832 voxels = 52 KB).
-//   * the 8 consumer warps read corners with LDS.128.  Mapping: 2 lanes per ray, lane c owns the x-corner x0 + c and all
-//     16 channels; the four 16-byte chunks of a voxel are read in an order rotated by the ray's index in its quarter-warp
+//   * a CTA (8 warps) marches a 16x8 pixel tile of one view in k-SLABS (runs of consecutive sample depths).  The samples of
+//     a slab form a frustum segment whose voxel footprint is bounded by the axis-aligned box of its 8 vertices (positions
+//     are multilinear in pixel and depth).  The brick is fetched from the packed volume as z-planes of a static in-plane
+//     shape, one cp.async.bulk.tensor (UTMALDG) per plane, into a 2-stage shared-memory ring; slab lengths adapt so that
+//     every brick fits its stage (<= 832 voxels = 52 KB).
+//   * a ninth warp is the producer: it waits for a stage to be released (empty mbarrier, one arrival per consumer warp),
+//     issues the copies of the next slab (planned while the previous copies were in flight) and plans the one after it.
+//     (Variant without a producer warp -- the last consumer warp to finish a slab refills the stage, 128 registers per
+//     thread -- measured slower, 0.370 vs 0.357 ms at cfg-2: the refill lands on the critical path of the slowest warp.)
+//   * corners are read with LDS.128.  Mapping: 2 lanes per ray, lane c owns the x-corner x0 + c and all 16 channels; the
+//     four 16-byte chunks of a voxel are read in an order rotated by the ray's index in its quarter-warp
 //     (chunk = i ^ (ray & 3)), so the 8 lanes of a shared-memory phase always hit 8 distinct 4-bank groups: x0 and x0+1
 //     are adjacent 64-byte records (opposite bank halves) and the four rays use four different chunk slots.  Every
-//     LDS.128 phase is therefore one conflict-free wavefront: 4 wavefronts per ray-sample, the minimum for 512 bytes,
-//     where the direct L1 gathers of raymarch_fwd_kernel need ~6.3 (one per distinct 128-byte line of a request).
-//   * each voxel crosses L2 -> SM about once per slab it is used in (bricks are shared by the 128 rays of the tile), and
-//     nothing is re-fetched through the L1 tag path.
+//     LDS.128 phase is one conflict-free wavefront: 4 wavefronts per ray-sample, the minimum for 512 bytes, where the
+//     direct L1 gathers of raymarch_fwd_kernel need ~6.3 (one per distinct 128-byte line of a request).
 //
-// A sample whose footprint is not completely inside the resident brick (possible only through rounding at the box faces or
-// a clipped box) takes the direct global path, so results never depend on the box arithmetic.  Density stays on the
-// global path (dens_quad: 32 bytes per sample against 512 for the features).
+// A sample whose footprint is not completely inside the resident brick (rounding at the box faces, clipped boxes) takes the
+// direct global path, so results never depend on the box arithmetic.  Density stays on the global path (dens_quad: 32
+// bytes per sample against 512 for the features), software-pipelined one sample ahead.
 #include <cstdlib>
 
-#include "async.cuh"
 #include "raymarch_common.cuh"
+#include "tensormap.cuh"
 
 namespace forge {
 
 using namespace async_;
 
-constexpr int kTW = 16, kTH = 8;                  // pixel tile of a CTA
-constexpr int kConsWarps = 8;                     // 8 warps x 16 rays x 2 lanes
-constexpr int kTmaThreads = 32 * (kConsWarps + 1);
-constexpr int kStages = 2;
-constexpr int kStageVox = 832;                    // voxels per stage (64 B each)
+constexpr int kTW = 16;                           // pixel tile of a CTA: 16 x (4 kWarpsY); 4 kWarpsY consumer warps + 1 producer
 constexpr int kSlabMax = 8;                       // most samples per slab
+constexpr int kMaxStages = 4;
+
+// Static in-plane box shapes of the tensor maps (voxels in x, y): a slab's brick is fetched as ez z-planes of the smallest
+// shape that covers its footprint, one cp.async.bulk.tensor (UTMALDG) per plane.  (Row-wise cp.async.bulk copies, ~53 per
+// slab, saturated the SM's TMA unit at ~50 cycles per request: ncu showed the producer warp 88 % busy issuing them.)
+constexpr int kNumBX = 4, kNumBY = 4;
+__constant__ int c_box_x[kNumBX] = {8, 10, 12, 16};
+__constant__ int c_box_y[kNumBY] = {6, 8, 12, 16};
+constexpr int kBoxX[kNumBX] = {8, 10, 12, 16};
+constexpr int kBoxY[kNumBY] = {6, 8, 12, 16};
+struct TmaMaps {
+    CUtensorMap m[kNumBX * kNumBY];      // index = iy * kNumBX + ix
+};
 
 struct SlabHeader {
     int ka, kb;          // sample range [ka, kb)
     int lx, ly, lz;      // box origin in padded voxel coordinates
-    int ex, ey, ez;      // box extent (0 = nothing resident)
+    int ex, ey, ez;      // box extent = pitches of the brick (0 = nothing resident)
+    int shape;           // tensor-map index
 };
 
 struct TmaSmem {
-    unsigned long long full[kStages], empty[kStages];
-    SlabHeader hdr[kStages];
+    unsigned long long full[kMaxStages], empty[kMaxStages];
+    SlabHeader hdr[8];                   // slab s lives in hdr[s & 7] (planned up to kStages + 1 slabs ahead)
     float cam[12];
     int kt0, kt1;
     float zs[kMaxP];
 };
-constexpr int kTmaSmemBytes = kStages * kStageVox * 64 + static_cast<int>(sizeof(TmaSmem));
+constexpr int tma_smem_bytes(int stages, int stage_vox) { return stages * stage_vox * 64 + static_cast<int>(sizeof(TmaSmem)); }
 
 struct Box {
     int lo[3], ex[3];
@@ -96,11 +108,15 @@ __device__ __forceinline__ void fma4(float* acc, float w, const float4 v) {
     acc[0] = a.x, acc[1] = a.y, acc[2] = b.x, acc[3] = b.y;
 }
 
-__global__ void __launch_bounds__(kTmaThreads, 2)
-raymarch_fwd_tma_kernel(const float* __restrict__ feat_pad, const float4* __restrict__ dens_quad,
+// kStages x kStageVox voxels (64 B each) of brick ring per CTA; two CTAs per SM
+template <int kStages, int kStageVox, int kWarpsY>
+__global__ void __launch_bounds__(32 * (4 * kWarpsY + 1), kWarpsY <= 2 ? 2 : 1)
+raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __restrict__ feat_pad,
+                        const float4* __restrict__ dens_quad,
                         const int* __restrict__ view2vol, const float* __restrict__ cam12, const float* __restrict__ zs_g,
                         float* __restrict__ out_feat, float* __restrict__ out_sil, float* __restrict__ out_depth, int D,
                         int H, int W, int Sh, int Sw, int P, int tiles_x, int interleave) {
+    constexpr int kConsWarps = 4 * kWarpsY, kTmaThreads = 32 * (kConsWarps + 1), kTH = 4 * kWarpsY;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw + kStages * kStageVox * 64);
     const uint32_t stage0 = smem_u32(smem_raw);
@@ -130,18 +146,15 @@ raymarch_fwd_tma_kernel(const float* __restrict__ feat_pad, const float4* __rest
     const long long v = view2vol[n];
     const float* fvol = feat_pad + v * (D + 2) * Hp * Wp * 16;
 
-    // ---- per-ray setup (consumer warps) and the tile's sample range ----
+    // ---- per-ray setup and the tile's sample range ----
     const int c = lane & 1, q = lane >> 1, rq = q & 3;
     const int j = tx * kTW + (warp & 3) * 4 + (q & 3);
-    const int i = ty * kTH + ((warp >> 2) & 1) * 4 + (q >> 2);
+    const int i = ty * kTH + ((warp >> 2) % kWarpsY) * 4 + (q >> 2);
     const bool valid = (warp < kConsWarps) && (i < Sh) && (j < Sw);
     Ray r;
-    r.k0 = 0;
-    r.k1 = 0;
-    if (warp < kConsWarps) {
-        r = make_ray(sm.cam, i, j, sm.zs, P, D, H, W);
-        if (!valid) r.k1 = 0;
-    }
+    r.k0 = r.k1 = 0;
+    if (warp < kConsWarps) r = make_ray(sm.cam, i, j, sm.zs, P, D, H, W);
+    if (!valid) r.k1 = 0;
     int kw0 = r.k1 > r.k0 ? r.k0 : P, kw1 = r.k1 > r.k0 ? r.k1 : 0;
 #pragma unroll
     for (int s = 16; s >= 2; s >>= 1) {
@@ -167,49 +180,67 @@ raymarch_fwd_tma_kernel(const float* __restrict__ feat_pad, const float4* __rest
         return;
     }
 
+    // ---- slab planning and brick copies (executed by whole warps; all lanes hold the same result) ----
+    const float u0 = static_cast<float>(tx * kTW) + 0.5f, u1 = static_cast<float>(min(tx * kTW + kTW, Sw) - 1) + 0.5f;
+    const float v0 = static_cast<float>(ty * kTH) + 0.5f, v1 = static_cast<float>(min(ty * kTH + kTH, Sh) - 1) + 0.5f;
+    const int zvol = static_cast<int>(v) * (D + 2);
+    // plan slab s starting at sample ka into hdr[s & 7]: lane L sizes the box of samples [ka, ka + 1 + L); the longest run
+    // whose brick (static in-plane shape x its z extent) fits a stage wins.  ka >= kt1 plans an empty end marker.
+    auto plan = [&](int s, int ka) {
+        const int cand = min(ka + 1 + min(lane, kSlabMax - 1), kt1);
+        Box mine;
+        mine.lo[0] = mine.lo[1] = mine.lo[2] = 0;
+        mine.ex[0] = mine.ex[1] = mine.ex[2] = 0;
+        if (ka < kt1) mine = slab_box(sm.cam, sm.zs, ka, cand, u0, u1, v0, v1, D, H, W);
+        int ix = 0, iy = 0;                                  // smallest static shape covering the footprint in x, y
+#pragma unroll
+        for (int e = 0; e < kNumBX - 1; ++e) ix += (mine.ex[0] > c_box_x[e]);
+#pragma unroll
+        for (int e = 0; e < kNumBY - 1; ++e) iy += (mine.ex[1] > c_box_y[e]);
+        const int bx = c_box_x[ix], by = c_box_y[iy];
+        const bool empty = mine.ex[0] == 0;
+        const unsigned fits = __ballot_sync(0xffffffffu, empty || bx * by * mine.ex[2] <= kStageVox) & ((1u << kSlabMax) - 1u);
+        const int pick = max(__ffs(~fits) - 1, 1) - 1;      // longest run of fitting candidates, at least one sample
+        if (lane == pick) {
+            SlabHeader h;
+            h.ka = ka, h.kb = (ka < kt1) ? cand : ka;
+            h.lx = mine.lo[0], h.ly = mine.lo[1], h.lz = mine.lo[2];
+            h.ex = empty ? 0 : bx, h.ey = empty ? 0 : by;
+            h.ez = empty ? 0 : min(mine.ex[2], kStageVox / (bx * by));   // a single sample too deep: clip (the rest gathers)
+            h.shape = iy * kNumBX + ix;
+            sm.hdr[s & 7] = h;
+        }
+        __syncwarp();
+    };
+    // issue the brick of (already planned) slab s into its stage
+    auto issue = [&](int s) {
+        const int st = s % kStages;
+        const SlabHeader h = sm.hdr[s & 7];
+        const uint32_t plane_bytes = static_cast<uint32_t>(h.ex * h.ey) * 64u;
+        if (lane == 0) {
+            if (h.ez > 0) mbar_arrive_expect_tx(&sm.full[st], plane_bytes * static_cast<uint32_t>(h.ez));
+            else mbar_arrive(&sm.full[st]);
+        }
+        __syncwarp();
+        const uint32_t dst0 = stage0 + static_cast<uint32_t>(st) * (kStageVox * 64);
+        if (lane < h.ez)
+            tma_load_4d(dst0 + static_cast<uint32_t>(lane) * plane_bytes, &maps.m[h.shape], 0, h.lx, h.ly, zvol + h.lz + lane,
+                        &sm.full[st]);
+    };
     if (warp == kConsWarps) {
-        // ================= producer warp: slab schedule + TMA bulk copies =================
-        const float u0 = static_cast<float>(tx * kTW) + 0.5f, u1 = static_cast<float>(min(tx * kTW + kTW, Sw) - 1) + 0.5f;
-        const float v0 = static_cast<float>(ty * kTH) + 0.5f, v1 = static_cast<float>(min(ty * kTH + kTH, Sh) - 1) + 0.5f;
-        int ka = kt0;
-        for (int it = 0; ka < kt1; ++it) {
-            const int st = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
-            mbar_wait(&sm.empty[st], ph ^ 1);
-            // greedy slab: extend while the box fits the stage (every lane computes the same thing: no broadcast needed)
-            int kb = ka + 1;
-            Box box = slab_box(sm.cam, sm.zs, ka, kb, u0, u1, v0, v1, D, H, W);
-            while (kb < kt1 && kb - ka < kSlabMax) {
-                const Box nb = slab_box(sm.cam, sm.zs, ka, kb + 1, u0, u1, v0, v1, D, H, W);
-                if (nb.vol() > kStageVox) break;
-                box = nb;
-                ++kb;
-            }
-            while (box.vol() > kStageVox) --box.ex[2];        // a single sample that does not fit: clip (the rest gathers directly)
-            const int rows = box.ex[1] * box.ex[2];
-            const uint32_t row_bytes = static_cast<uint32_t>(box.ex[0]) * 64u;
-            if (lane == 0) {
-                SlabHeader h;
-                h.ka = ka, h.kb = kb;
-                h.lx = box.lo[0], h.ly = box.lo[1], h.lz = box.lo[2];
-                h.ex = box.ex[0], h.ey = box.ex[1], h.ez = box.ex[2];
-                sm.hdr[st] = h;
-                if (rows > 0) mbar_arrive_expect_tx(&sm.full[st], row_bytes * static_cast<uint32_t>(rows));
-                else mbar_arrive(&sm.full[st]);
-            }
-            __syncwarp();
-            const uint32_t dst0 = stage0 + static_cast<uint32_t>(st) * (kStageVox * 64);
-            for (int rw = lane; rw < rows; rw += 32) {
-                const int zz = rw / box.ex[1], yy = rw - zz * box.ex[1];
-                const float* src = fvol + ((static_cast<long long>(box.lo[2] + zz) * Hp + (box.lo[1] + yy)) * Wp + box.lo[0]) * 16;
-                bulk_g2s(dst0 + static_cast<uint32_t>(rw) * row_bytes, src, row_bytes, &sm.full[st]);
-            }
-            ka = kb;
+        // ================= producer warp =================
+        // only the wait for a free stage and the issue sit on the critical path: slab s + 1 is planned right after slab s
+        // has been issued, i.e. while its copies are in flight and the consumers are busy
+        if (lane < kNumBX * kNumBY) prefetch_tensormap(&maps.m[lane]);
+        plan(0, kt0);
+        for (int s = 0; sm.hdr[s & 7].ka < kt1; ++s) {
+            mbar_wait(&sm.empty[s % kStages], ((s / kStages) & 1) ^ 1);
+            issue(s);
+            plan(s + 1, sm.hdr[s & 7].kb);
         }
         return;
     }
 
-    // ================= consumer warps =================
     const float4* qv = dens_quad + v * (D + 2) * Hq * Wq;
     const int row_y = Wp * 16, row_z = Hp * Wp * 16;          // float strides of the padded feature volume
     uint32_t choff[4];                                        // byte offset of the chunk this lane reads i-th
@@ -221,24 +252,36 @@ raymarch_fwd_tma_kernel(const float* __restrict__ feat_pad, const float4* __rest
     for (int e = 0; e < 16; ++e) acc[e] = 0.f;
     float T = 1.f, depth = 0.f;
 
-    int k = kt0;
-    for (int it = 0; k < kt1; ++it) {
-        const int st = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&sm.full[st], ph);
-        const SlabHeader h = sm.hdr[st];
+    // Software pipeline, one sample ahead: the footprint of sample k + 1 is computed and its density quad requested before
+    // the feature work of sample k, so the global-load latency hides behind the 16 LDS.128 + 32 FFMA2 of the current sample.
+    auto fetch = [&](int kk, Foot& f, float4& d4) -> bool {     // footprint of sample kk + its density quad (lane c: plane z0 + c)
+        f = sample_foot(r, sm.zs[kk], D, H, W);
+        const bool act = f.in && (kk >= r.k0) && (kk < r.k1);
+        if (act) d4 = __ldg(qv + (static_cast<long long>(f.z0 + 1 + c) * Hq + (f.y0 + 1)) * Wq + (f.x0 + 1));
+        return act;
+    };
+    Foot fn;
+    float4 d4n = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool actn = false;
+    if (kw1 > kw0) actn = fetch(max(kt0, kw0), fn, d4n);
+
+    for (int s = 0;; ++s) {
+        const int st = s % kStages;
+        mbar_wait(&sm.full[st], (s / kStages) & 1);
+        const SlabHeader h = sm.hdr[s & 7];
         const uint32_t brick = stage0 + static_cast<uint32_t>(st) * (kStageVox * 64);
         const int kend = min(h.kb, kw1);
-        for (k = max(h.ka, kw0); k < kend; ++k) {
+        for (int k = max(h.ka, kw0); k < kend; ++k) {
             const float z = sm.zs[k];
-            const Foot f = sample_foot(r, z, D, H, W);
-            const bool act = f.in && (k >= r.k0) && (k < r.k1);
+            const Foot f = fn;
+            const bool act = actn;
+            const float4 d4 = d4n;
+            if (k + 1 < kw1) actn = fetch(k + 1, fn, d4n);
             const float w00 = __fmul_rn(f.wx0, f.wy0), w10 = __fmul_rn(f.wx1, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1),
                         w11 = __fmul_rn(f.wx1, f.wy1);
             float part = 0.f;
             if (act) {          // density: lane c owns plane z0 + c (one 16-byte quad = its four x/y corners)
                 const float wz = c ? f.wz1 : f.wz0;
-                const float4 d4 = __ldg(qv + (static_cast<long long>(f.z0 + 1 + c) * Hq + (f.y0 + 1)) * Wq + (f.x0 + 1));
                 part = __fmul_rn(w00, wz) * d4.x;
                 part = fmaf(__fmul_rn(w10, wz), d4.y, part);
                 part = fmaf(__fmul_rn(w01, wz), d4.z, part);
@@ -277,9 +320,9 @@ raymarch_fwd_tma_kernel(const float* __restrict__ feat_pad, const float4* __rest
             }
             T = T * (1.f - sigma);
         }
-        k = h.kb;
+        if (h.kb >= kt1) break;                               // that was the last slab
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[st]);
+        if (lane == 0) mbar_arrive(&sm.empty[st]);            // release the stage to the producer
     }
 
     // ---- combine the two x-corner halves of the pair, store (acc[4 e + t] is channel 4 (e ^ rq) + t) ----
@@ -299,16 +342,51 @@ raymarch_fwd_tma_kernel(const float* __restrict__ feat_pad, const float4* __rest
     }
 }
 
+template <int kStages, int kStageVox, int kWarpsY>
+static int tma_launch_cfg(const char* fn, const TmaMaps& maps, const float* feat_pad, const float4* dens_quad,
+                          const int* view2vol, const float* cam12, const float* zs, float* out_feat, float* out_sil,
+                          float* out_depth, int N, int V, int D, int H, int W, int S_h, int S_w, int P, cudaStream_t st) {
+    constexpr int bytes = tma_smem_bytes(kStages, kStageVox), kTH = 4 * kWarpsY, threads = 32 * (4 * kWarpsY + 1);
+    static_assert((kWarpsY <= 2 ? 2 : 1) * bytes <= 227 * 1024 && kStages <= kMaxStages, "the CTAs of an SM must fit");
+    static_assert(kStageVox >= 16 * 16, "a stage must hold one plane of the largest shape");
+    if (int e = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(raymarch_fwd_tma_kernel<kStages, kStageVox, kWarpsY>), bytes))
+        return e;
+    const int tiles_x = (S_w + kTW - 1) / kTW, tiles_y = (S_h + kTH - 1) / kTH;
+    dim3 grid(tiles_x * tiles_y, N);
+    raymarch_fwd_tma_kernel<kStages, kStageVox, kWarpsY><<<grid, threads, bytes, st>>>(
+        maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, D, H, W, S_h, S_w, P, tiles_x,
+        interleave_views(V, D, H, W));
+    return check_launch(fn);
+}
+
 int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4* dens_quad, const int* view2vol,
                             const float* cam12, const float* zs, float* out_feat, float* out_sil, float* out_depth, int N,
                             int V, int D, int H, int W, int S_h, int S_w, int P, cudaStream_t st) {
-    if (int e = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(raymarch_fwd_tma_kernel), kTmaSmemBytes)) return e;
-    const int tiles_x = (S_w + kTW - 1) / kTW, tiles_y = (S_h + kTH - 1) / kTH;
-    dim3 grid(tiles_x * tiles_y, N);
-    raymarch_fwd_tma_kernel<<<grid, kTmaThreads, kTmaSmemBytes, st>>>(feat_pad, dens_quad, view2vol, cam12, zs, out_feat,
-                                                                       out_sil, out_depth, D, H, W, S_h, S_w, P, tiles_x,
-                                                                       interleave_views(V, D, H, W));
-    return check_launch(fn);
+    static const int ring = [] {                // tuning knob (development): ring shape "stages x voxels per stage"
+        const char* e = getenv("FORGE_K1T_RING");
+        return e ? atoi(e) : 2;
+    }();
+    // tensor maps over feat_pad viewed as [V (D+2)] [H+2] [W+2] [16] fp32, one per static in-plane box shape (host-side
+    // encode, ~1 us each; passed to the kernel as __grid_constant__ parameters: no device allocation)
+    alignas(64) TmaMaps maps;
+    const unsigned long long dims[4] = {16ull, static_cast<unsigned long long>(W + 2), static_cast<unsigned long long>(H + 2),
+                                        static_cast<unsigned long long>(D + 2) * V};
+    const unsigned long long strides[3] = {64ull, 64ull * (W + 2), 64ull * (W + 2) * (H + 2)};
+    for (int iy = 0; iy < kNumBY; ++iy)
+        for (int ix = 0; ix < kNumBX; ++ix) {
+            const unsigned box[4] = {16u, static_cast<unsigned>(kBoxX[ix]), static_cast<unsigned>(kBoxY[iy]), 1u};
+            if (int e = encode_tensor_map(fn, &maps.m[iy * kNumBX + ix], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, feat_pad, dims, strides,
+                                          box, CU_TENSOR_MAP_SWIZZLE_NONE))
+                return e;
+        }
+#define FORGE_K1T(S, VOX, WY)                                                                                                \
+    return tma_launch_cfg<S, VOX, WY>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D, H, \
+                                      W, S_h, S_w, P, st)
+    if (ring == 3) FORGE_K1T(3, 552, 2);
+    if (ring == 5) FORGE_K1T(2, 1700, 4);         // 16 x 16 pixel tile, one CTA per SM, twice the slab length
+    if (ring == 6) FORGE_K1T(3, 1130, 4);
+    FORGE_K1T(2, 832, 2);
+#undef FORGE_K1T
 }
 
 }  // namespace forge
