@@ -49,6 +49,57 @@ class ConvGRU_3D(nn.Module):
         self.fusion_norm = nn.BatchNorm3d(hidden_size)
         self.fusion_conv = nn.Sequential(*_conv_bn_act(input_size, input_size), *_conv_bn_act(input_size, input_size))
 
+    # ---- tensor-core path (forge_conv3d_tc): bf16 operands, fp32 accumulation and state; inference only ----
+    def tc_eligible(self, x):
+        """eval mode, no autograd graph wanted, one layer of 128 -> 128 channels on a grid the kernel tiles (z, y % 4, x % 8)"""
+        b, t, c, d, h, w = x.shape
+        return (x.is_cuda and not self.training and self.n_layers == 1 and c % 64 == 0 and self.hidden_size == 128
+                and c == self.hidden_size and d % 4 == 0 and h % 4 == 0 and w % 8 == 0
+                and not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))))
+
+    def _tc_packs(self):
+        tensors = list(self.parameters()) + list(self.buffers())
+        key = tuple((p.data_ptr(), p._version) for p in tensors)
+        if getattr(self, '_tc_cache', None) is None or self._tc_cache[0] != key:
+            def bn_fold(conv, bn):
+                s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                return s.float().contiguous(), ((conv.bias - bn.running_mean) * s + bn.bias).float().contiguous()
+            with torch.no_grad():
+                cell = self.cells[0]
+                fc = self.fusion_conv
+                s1, b1 = bn_fold(fc[0], fc[1])
+                s2, b2 = bn_fold(fc[3], fc[4])
+                ns = (self.fusion_norm.weight / torch.sqrt(self.fusion_norm.running_var + self.fusion_norm.eps)).float().contiguous()
+                nb = (self.fusion_norm.bias - self.fusion_norm.running_mean * ns).float().contiguous()
+                packs = dict(w1=ops.pack_conv3d_weights(fc[0].weight), s1=s1, b1=b1,
+                             w2=ops.pack_conv3d_weights(fc[3].weight), s2=s2, b2=b2,
+                             wg=ops.pack_conv3d_weights(cell.conv_gate.weight), bg=cell.conv_gate.bias.float().contiguous(),
+                             wo=ops.pack_conv3d_weights(cell.out_gate.weight), bo=cell.out_gate.bias.float().contiguous(),
+                             ns=ns, nb=nb)
+            self._tc_cache = (key, packs)
+        return self._tc_cache[1]
+
+    def forward_tc(self, x):
+        """fuse(x) = fusion_norm(GRU over the views, h0 = fusion_conv(mean_t x)) (reference models/encoder.py:59-63,
+        models/fusion.py:71-95) with every convolution and the gate arithmetic on the tensor cores: 2 + 2 t launches, no
+        cat / sigmoid / tanh / lerp passes, the view sequence is read as bf16 straight from K2's channels-last output."""
+        pk = self._tc_packs()
+        b, t = x.shape[:2]
+        xb = x.to(torch.bfloat16)                                   # keeps the [b,t,D,H,W,C] memory order of K2's output
+        if not xb.permute(0, 1, 3, 4, 5, 2).is_contiguous():
+            xb = xb.permute(0, 1, 3, 4, 5, 2).contiguous().permute(0, 1, 5, 2, 3, 4)
+        xm = x.float().mean(dim=1)
+        _, a16, _ = ops.conv3d_tc(xm, pk['w1'], 'plain', pk['b1'], scale=pk['s1'], lrelu=True, want_f32=False, want_bf16=True)
+        h, h16, _ = ops.conv3d_tc(a16, pk['w2'], 'plain', pk['b2'], scale=pk['s2'], lrelu=True, want_f32=True, want_bf16=True)
+        out = None
+        for i in range(t):
+            x_t = xb[:, i]
+            last = i == t - 1
+            u, hr, _ = ops.conv3d_tc(x_t, pk['wg'], 'gate', pk['bg'], h2=h16, h_state=h)
+            h, h16, out = ops.conv3d_tc(x_t, pk['wo'], 'out', pk['bo'], h2=hr, h_state=h, u_in=u, scale=pk['ns'],
+                                        norm_shift=pk['nb'], want_bf16=not last, want_norm=last)
+        return out
+
     def forward(self, x, hidden=None):
         """x [b,t,c,d,h,w] (view sequence); hidden: optional list of initial states, one per layer -> fusion_norm(h_T)"""
         states = list(hidden) if hidden else [None] * self.n_layers

@@ -644,3 +644,59 @@ def gru_out(o, g, h):
     if g.dtype not in (torch.float32, torch.bfloat16):
         g = g.float()
     return _GruOut.apply(o.to(g.dtype), g, h.float())
+
+
+# ---- tensor-core 3-D convolution with fused ConvGRU epilogues (inference / pose refinement) --------------------------------
+def pack_conv3d_weights(weight):
+    """[Cout, Cin, 3, 3, 3] fp32 -> bf16 [27][Cin / 64][Cout][64] for forge_conv3d_tc (tap index (dz*3 + dy)*3 + dx)."""
+    Cout, Cin = weight.shape[:2]
+    if tuple(weight.shape[2:]) != (3, 3, 3) or Cin % 64:
+        raise ValueError("forge_conv3d_tc needs a 3x3x3 kernel and Cin a multiple of 64 (got %s)" % (tuple(weight.shape),))
+    w = weight.detach().float().permute(2, 3, 4, 1, 0).reshape(27, Cin // 64, 64, Cout).permute(0, 1, 3, 2)
+    return w.contiguous().to(torch.bfloat16)
+
+
+def _bf16_cl(t):
+    """[B,C,D,H,W] (any strides) -> bf16 tensor whose memory is [B][D][H][W][C] with dense inner dims; returns (tensor, batch stride)"""
+    B, C, D, H, W = t.shape
+    want = (1, H * W * C, W * C, C)
+    ok = t.dtype == torch.bfloat16 and all(t.shape[i + 1] == 1 or t.stride(i + 1) == want[i] for i in range(4))
+    if not ok:
+        t = t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    return t, (t.stride(0) if B > 1 else C * D * H * W)
+
+
+def conv3d_tc(x, wpack, mode, shift, h2=None, scale=None, lrelu=False, norm_shift=None, h_state=None, u_in=None,
+              want_f32=True, want_bf16=False, want_norm=False, max_ctas=0):
+    """forge_conv3d_tc on [B,C,D,H,W] tensors (channels-last memory).  Returns (out_f32, out_bf16, out_norm) as
+    [B,Cg,D,H,W] channels-last views (None where not requested).  mode: 'plain' | 'gate' | 'out' (see forge_b200.h)."""
+    _require_cuda(x, wpack, shift)
+    B, Cx, D, H, W = x.shape
+    xb, xbs = _bf16_cl(x)
+    hb, hbs, Ch = None, 0, 0
+    if h2 is not None:
+        hb, hbs = _bf16_cl(h2)
+        Ch = h2.shape[1]
+    Cout = wpack.shape[2]
+    m = {'plain': 0, 'gate': 1, 'out': 2}[mode]
+    Cg = Cout // 2 if m == 1 else Cout
+    dev = x.device
+
+    def cl(dtype):
+        return torch.empty(B, D, H, W, Cg, dtype=dtype, device=dev)
+
+    def dense_f32(t):       # fp32 state tensors must be dense channels-last
+        if t is None:
+            return None
+        tt = t.permute(0, 2, 3, 4, 1)
+        return tt if (tt.is_contiguous() and t.dtype == torch.float32) else tt.float().contiguous()
+    hs, ui = dense_f32(h_state), dense_f32(u_in)
+    o32 = cl(torch.float32) if (want_f32 or m != 0) else None
+    o16 = cl(torch.bfloat16) if (want_bf16 or m == 1) else None
+    on = cl(torch.float32) if want_norm else None
+    with torch.cuda.device(dev):
+        _lib.call("forge_conv3d_tc", _ptr(xb), xbs, Cx, _ptr(hb), hbs, Ch, _ptr(wpack), m, int(bool(lrelu)), _ptr(scale),
+                  _ptr(shift), _ptr(norm_shift), _ptr(hs), _ptr(ui), _ptr(o32), _ptr(o16), _ptr(on), B, D, H, W, Cout,
+                  int(max_ctas), _stream(x))
+    view = lambda t: None if t is None else t.permute(0, 4, 1, 2, 3)     # noqa: E731
+    return view(o32), view(o16), view(on)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 13
+#define FORGE_ABI_VERSION 14
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -231,6 +231,26 @@ int forge_gru_out_bwd(const float* d_h_new, const void* o, const void* g, int og
  * against ATen's GridSampler.h unnormalize + floor. */
 int forge_sample_points(const float* pts, int M, int D, int H, int W, int align_corners, int* base,
                         unsigned char* mask, void* stream);
+
+/* ---- 3x3x3 convolution on the tcgen05 tensor cores with fused ConvGRU epilogues ----------------------------------
+ * Replaces the cuDNN convolutions and the elementwise chain of models/fusion.py:18-35 (ConvGRUCell_3D) and :61-68
+ * (fusion_conv) on the inference / pose-refinement path.  bf16 operands, fp32 accumulation (TMEM), fp32 state.
+ *
+ *   x  [B][D][H][W][Cx] bf16 channels-last, batch stride x_batch_stride ELEMENTS (a view of a [B][t][...] sequence is fine)
+ *   h2 optional second source [B][D][H][W][Ch] bf16 (the convolution runs over cat(x, h2) without materialising it)
+ *   wpack [27][(Cx + Ch) / 64][Cout][64] bf16: w[co][ci][dz][dy][dx] at [(dz*3+dy)*3+dx][ci / 64][co][ci % 64]
+ *   D, H multiples of 4, W a multiple of 8; Cx, Ch multiples of 64; Cout 128 or 256
+ *   mode 0 (plain): y = act(acc * scale + shift), scale nullable (= 1), act = LeakyReLU(0.01) when lrelu != 0;
+ *                   out_f32 / out_bf16 [B][D][H][W][Cout] (either may be NULL)
+ *   mode 1 (gate):  Cout = 2C; u = sigmoid(acc[:, :C] + shift), r = sigmoid(acc[:, C:] + shift); out_f32 = u [..][C],
+ *                   out_bf16 = h_state * r [..][C]           (h_state fp32 [B][D][H][W][C])
+ *   mode 2 (out):   Cout = C; c = tanh(acc + shift); h' = h_state (1 - u_in) + c u_in; out_f32 = h', out_bf16 = h' (nullable),
+ *                   out_norm = h' * scale + norm_shift (nullable; fusion_norm in eval mode)
+ *   max_ctas: 0 = one persistent CTA per SM */
+int forge_conv3d_tc(const void* x, long long x_batch_stride, int Cx, const void* h2, long long h_batch_stride, int Ch,
+                    const void* wpack, int mode, int lrelu, const float* scale, const float* shift,
+                    const float* norm_shift, const float* h_state, const float* u_in, float* out_f32, void* out_bf16,
+                    float* out_norm, int B, int D, int H, int W, int Cout, int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

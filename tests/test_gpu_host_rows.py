@@ -111,3 +111,25 @@ def test_pose_estimator3d_model_train_mode_heads_match_reference():
     assert _err(m.encoder_3d.density_head[1].running_mean, g['dens_bn_mean']) <= 1e-4
     assert _err(m.encoder_3d.features_head[4].running_var, g['feat_bn_var']) <= 1e-4
     assert _err(m.render.conv_rgb[1].running_mean, g['rgb_bn_mean']) <= 1e-4
+
+
+def test_fuse_on_tensor_cores_matches_reference_within_bf16_tolerance():
+    """Encoder3D.fuse through forge_conv3d_tc (bf16 operands, fp32 accumulation / state) against the fp32 reference fixture;
+    tolerance = bf16 operand rounding through 2 + 2 x 3 convolutions (measured 4e-3 of the output range)."""
+    g = load_golden("encoder_small")
+    s = g['seed']
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = seeded.load_seeded(Encoder3D(syn.make_config()), s).to(DEV).eval()
+    m.channels_last_3d_()
+    m.compute_dtype = torch.bfloat16
+    views = seeded.seeded_tensor(s, 'views', (1, 3, 128, 8, 8, 8)).to(DEV)
+    views = views.permute(0, 1, 3, 4, 5, 2).contiguous().permute(0, 1, 5, 2, 3, 4)
+    with torch.no_grad():
+        assert m.fusion_feature.tc_eligible(views)
+        fused = m.fuse(views)
+    assert fused.shape == g['fused'].shape
+    assert _err(fused, g['fused']) <= 2e-2
+    # with a graph wanted the module falls back to autograd-capable convolutions
+    v2 = views.clone().requires_grad_(True)
+    assert not m.fusion_feature.tc_eligible(v2)
