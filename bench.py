@@ -233,8 +233,10 @@ def k2_setup(cfg, objects, views, C, n, seed, dev):
     del vox
     gx, gy, gz, gmax = rot._device_axes(n, n, n, dev)
     A = ops.pose_affine(poses)
-    jobs = rot._jobs(objects, views, dev, None)
-    return vcl, A, jobs, gx, gy, gz, gmax, torch.empty_like(vcl)
+    # transform jobs only: the pipeline aliases view 0 of the input instead of copying it (Rotate_world.forward_views)
+    jobs = rot._jobs_aliased(objects, views, dev, None)
+    out = torch.empty(objects * (views - 1), n, n, n, C, device=dev)
+    return vcl, A, jobs, gx, gy, gz, gmax, out
 
 
 def k2_launch(lib_call, vcl, A, jobs, gx, gy, gz, gmax, out_cl, M, C, n, dev):
@@ -331,9 +333,9 @@ def run_forge(args, rank, world, local_rank):
         # ---- secondary: K2 (the HBM-bound kernel of the path) on cfg-2's fusion grid, same run ------------
         Cr, nr, tr = 128, D // 2, CFG['views']
         k2 = k2_setup(cfg, V, tr, Cr, nr, 100 + rank, dev)
-        k2_avg_ms = timed_launches(lambda: k2_launch(_lib.call, *k2, V * tr, Cr, nr, dev), flush, dev)
-        k2_bytes_moved = 2 * k2[0].numel() * 4                              # incl. the view-0 passthrough copies
+        k2_avg_ms = timed_launches(lambda: k2_launch(_lib.call, *k2, V * (tr - 1), Cr, nr, dev), flush, dev)
         k2_bytes = 2 * V * (tr - 1) * Cr * nr ** 3 * 4                      # read + write per TRANSFORM
+        k2_bytes_moved = k2_bytes                                           # view 0 is aliased, not copied
         del k2
 
         # ---- secondary: the tensor-core (bf16, tcgen05) decoder on the raymarcher's output, same run --------------
@@ -346,6 +348,17 @@ def run_forge(args, rank, world, local_rank):
         dec_flops = 2.0 * 6104 * N * (2 * S) ** 2          # MACs per output pixel: 16*16*9 + 8*16*25 + 3*8*25
         model.decoder_dtype = None
         del rgb
+
+        # ---- secondary: the ConvGRU gate convolution (256 -> 256 ch, 3^3 taps, 32^3 voxels x 4 objects) on tcgen05, same run ----
+        gC, gn = 128, D // 2
+        gx_ = torch.randn(V, gn, gn, gn, gC, device=dev).to(torch.bfloat16).permute(0, 4, 1, 2, 3)
+        gh_ = torch.randn(V, gn, gn, gn, gC, device=dev).permute(0, 4, 1, 2, 3)
+        gh16 = gh_.to(torch.bfloat16)
+        gw = ops.pack_conv3d_weights(torch.randn(2 * gC, 2 * gC, 3, 3, 3, device=dev) / (27 * 2 * gC) ** 0.5)
+        gb = torch.zeros(2 * gC, device=dev)
+        gru_avg_ms = timed_launches(lambda: ops.conv3d_tc(gx_, gw, 'gate', gb, h2=gh16, h_state=gh_), flush, dev)
+        gru_flops = 2.0 * V * gn ** 3 * (2 * gC) * 27 * (2 * gC)
+        del gx_, gh_, gh16, gw
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- end to end: pinned host inputs -> H2D -> public API -> D2H, everything timed ----------
@@ -436,17 +449,17 @@ def run_forge(args, rank, world, local_rank):
                 "unpipelined_api": "VolRender.render_features, one step at a time on one stream",
                 "gpu_launches": e2e_launches},
         "gpu_launches": n_launch,
-        "roofline": {"bound": "hbm", "kernel": "raymarch_fwd_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+        "roofline": {"bound": "hbm", "kernel": "raymarch_fwd_tma_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                      "algorithmic_bytes": algorithmic_bytes_k1(), "kernel_ms": k1_avg_s * 1e3,
                      "executed_samples": n_exec, "executed_fraction": n_exec / float(rays * P),
                      "fp32_tflops": n_exec * FLOPS_PER_SAMPLE / k1_avg_s / 1e12,
                      "fp32_tflops_note": "366 FLOP per EXECUTED sample (samples outside the volume are skipped exactly and not counted)",
-                     "note": "K1 is bound by the L1 data pipe (register write-back of the gathered corners), not by "
-                             "HBM (SURVEY 8d: 82 FLOP/B); bytes are the distinct-volume figure; see roofline_rotate for the "
-                             "HBM-bound kernel of the path"},
-        "roofline_rotate": {"bound": "hbm", "kernel": "rotate_fwd_kernel (K2, %d transforms + %d passthrough views of 128x%d^3, channels-last)"
-                            % (V * (CFG['views'] - 1), V, CFG['vol'] // 2),
+                     "note": "K1 (TMA-staged bricks in shared memory, conflict-free LDS.128 corner reads) is bound by shared-memory "
+                             "latency / instruction issue, not by HBM (SURVEY 8d: 82 FLOP/B); bytes are the distinct-volume figure; "
+                             "see roofline_rotate for the HBM-bound kernel of the path and roofline_fusion for the tensor-core one"},
+        "roofline_rotate": {"bound": "hbm", "kernel": "rotate_fwd_kernel (K2, %d transforms of 128x%d^3, channels-last; view 0 aliased, not copied)"
+                            % (V * (CFG['views'] - 1), CFG['vol'] // 2),
                             "achieved": k2_bytes / (k2_avg_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": k2_bytes / (k2_avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_kind": peak_kind,
                             "algorithmic_bytes": k2_bytes, "bytes_moved": k2_bytes_moved,
@@ -461,6 +474,13 @@ def run_forge(args, rank, world, local_rank):
                              "algorithmic_flops": dec_flops, "kernel_ms": dec_avg_ms,
                              "note": "secondary line: useful conv FLOPs (N = 16/8/3 output channels); the binding unit is the "
                                      "shared-memory operand path of the MMAs, see DESIGN.md"},
+        "roofline_fusion": {"bound": "tensor", "kernel": "conv3d_tc_kernel<256> (ConvGRU conv_gate as a tcgen05 implicit GEMM: M = %d voxels, "
+                            "N = 256, K = 27 x 256; bf16 in / fp32 accumulate in TMEM; sigmoid / h*r epilogue fused)" % (V * gn ** 3),
+                            "achieved": gru_flops / (gru_avg_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                            "frac": gru_flops / (gru_avg_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "peak_kind": peak_kind,
+                            "algorithmic_flops": gru_flops, "kernel_ms": gru_avg_ms,
+                            "note": "secondary line: the FLOP-dominant kernel of the fusion stage (reference models/fusion.py:29), rank 0, "
+                                    "timed in the same run through the Python op (output allocation + tensor-map encode included)"},
         "clocks": clocks,
     }
     out.update(extra)
@@ -545,9 +565,9 @@ def cfg4_leg(_lib, ops, dev, flush, peaks, peak_kind):
     n_exec = executed_samples(cam12, zs, S, D)
     del fp, dq, o_feat, inp
     k2 = k2_setup(cfg, b, t, 128, D // 2, 17, dev)
-    k2_ms = timed_launches(lambda: k2_launch(_lib.call, *k2, b * t, 128, D // 2, dev), flush, dev, reps=5, warm=2)
+    k2_ms = timed_launches(lambda: k2_launch(_lib.call, *k2, b * (t - 1), 128, D // 2, dev), flush, dev, reps=5, warm=2)
     k2_bytes = 2 * b * (t - 1) * 128 * (D // 2) ** 3 * 4
-    k2_moved = 2 * k2[0].numel() * 4
+    k2_moved = k2_bytes
     del k2
     torch.cuda.empty_cache()
     hb = peaks["hbm_gbs"]

@@ -79,7 +79,14 @@ class Encoder3D(nn.Module):
         if self.compute_dtype == torch.bfloat16 and self.tc_fusion and self.fusion_feature.tc_eligible(x):
             return self.fusion_feature.forward_tc(x)        # tcgen05 convolutions with fused gate epilogues (inference)
         with self._amp():
-            return self.fusion_feature(x, [self.fusion_feature.fusion_conv(x.mean(dim=1))]).float()
+            if isinstance(x, (list, tuple)):        # per-view tensors (Rotate_world.forward_views: no view-0 copy)
+                mean = x[0]
+                for v in x[1:]:
+                    mean = mean + v
+                mean = mean / len(x)
+            else:
+                mean = x.mean(dim=1)
+            return self.fusion_feature(x, [self.fusion_feature.fusion_conv(mean)]).float()
 
     def forward(self, x):
         raise NotImplementedError

@@ -52,10 +52,13 @@ class ConvGRU_3D(nn.Module):
     # ---- tensor-core path (forge_conv3d_tc): bf16 operands, fp32 accumulation and state; inference only ----
     def tc_eligible(self, x):
         """eval mode, no autograd graph wanted, one layer of 128 -> 128 channels on a grid the kernel tiles (z, y % 4, x % 8)"""
-        b, t, c, d, h, w = x.shape
-        return (x.is_cuda and not self.training and self.n_layers == 1 and c % 64 == 0 and self.hidden_size == 128
-                and c == self.hidden_size and d % 4 == 0 and h % 4 == 0 and w % 8 == 0
-                and not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))))
+        views = list(x) if isinstance(x, (list, tuple)) else None
+        x0 = views[0] if views else x[:, 0]
+        b, c, d, h, w = x0.shape
+        needs_graph = torch.is_grad_enabled() and (any(v.requires_grad for v in (views or [x])) or
+                                                    any(p.requires_grad for p in self.parameters()))
+        return (x0.is_cuda and not self.training and not needs_graph and self.n_layers == 1 and c % 64 == 0 and self.hidden_size == 128
+                and c == self.hidden_size and d % 4 == 0 and h % 4 == 0 and w % 8 == 0)
 
     def _tc_packs(self):
         tensors = list(self.parameters()) + list(self.buffers())
@@ -84,16 +87,18 @@ class ConvGRU_3D(nn.Module):
         models/fusion.py:71-95) with every convolution and the gate arithmetic on the tensor cores: 2 + 2 t launches, no
         cat / sigmoid / tanh / lerp passes, the view sequence is read as bf16 straight from K2's channels-last output."""
         pk = self._tc_packs()
-        b, t = x.shape[:2]
-        xb = x.to(torch.bfloat16)                                   # keeps the [b,t,D,H,W,C] memory order of K2's output
-        if not xb.permute(0, 1, 3, 4, 5, 2).is_contiguous():
-            xb = xb.permute(0, 1, 3, 4, 5, 2).contiguous().permute(0, 1, 5, 2, 3, 4)
-        xm = x.float().mean(dim=1)
+        views = list(x) if isinstance(x, (list, tuple)) else list(x.unbind(dim=1))
+        t = len(views)
+        xb = [v.to(torch.bfloat16) for v in views]                 # .to keeps K2's channels-last memory order
+        xm = views[0].float()
+        for v in views[1:]:
+            xm = xm + v
+        xm = xm / t
         _, a16, _ = ops.conv3d_tc(xm, pk['w1'], 'plain', pk['b1'], scale=pk['s1'], lrelu=True, want_f32=False, want_bf16=True)
         h, h16, _ = ops.conv3d_tc(a16, pk['w2'], 'plain', pk['b2'], scale=pk['s2'], lrelu=True, want_f32=True, want_bf16=True)
         out = None
         for i in range(t):
-            x_t = xb[:, i]
+            x_t = xb[i]
             last = i == t - 1
             u, hr, _ = ops.conv3d_tc(x_t, pk['wg'], 'gate', pk['bg'], h2=h16, h_state=h)
             h, h16, out = ops.conv3d_tc(x_t, pk['wo'], 'out', pk['bo'], h2=hr, h_state=h, u_in=u, scale=pk['ns'],
@@ -103,7 +108,7 @@ class ConvGRU_3D(nn.Module):
     def forward(self, x, hidden=None):
         """x [b,t,c,d,h,w] (view sequence); hidden: optional list of initial states, one per layer -> fusion_norm(h_T)"""
         states = list(hidden) if hidden else [None] * self.n_layers
-        seq = x.unbind(dim=1)
+        seq = list(x) if isinstance(x, (list, tuple)) else x.unbind(dim=1)
         h = None
         for cell, h in zip(self.cells, states):
             outs = []

@@ -30,6 +30,14 @@ def sequence_from_distance(trans):
     return idxs
 
 
+def _view0_first(idxs):
+    """the sorted view order with view 0 moved to slot 0 (where sequence_from_distance puts it anyway: its distance to itself
+    is exactly 0; an exact tie with another view is resolved in favour of view 0); no host synchronisation"""
+    t = idxs.shape[1]
+    keys = torch.arange(1, t + 1, device=idxs.device).expand_as(idxs).masked_fill(idxs == 0, 0)
+    return idxs.gather(1, torch.argsort(keys, dim=1))
+
+
 def chose_selected(tensor, idxs):
     """tensor [b,t,...], idxs [b,t] -> per-object gather along t (reference :161-168)"""
     assert tensor.shape[0] == len(idxs)
@@ -114,7 +122,9 @@ class FORGE(nn.Module):
     def reconstruct(self, features_raw, camPoses_cv2, idxs):
         """per-view volumes + poses -> fused render volumes (features [b,16,2D..], densities [b,1,2D..])"""
         D = features_raw.shape[3]
-        features_transformed = self.rotate(voxels=features_raw, camPoses_cv2=camPoses_cv2, grid_size=D, order=idxs)
+        # per-view tensors: slot 0 aliases view 0 of the input (no passthrough copy); view 0 is the nearest view to itself
+        idxs = _view0_first(idxs)
+        features_transformed = self.rotate.forward_views(voxels=features_raw, camPoses_cv2=camPoses_cv2, grid_size=D, order=idxs)
         features_mv = self.encoder_3d.fuse(features_transformed)
         densities_mv = self.encoder_3d.get_density3D(features_mv)
         features_mv = self.encoder_3d.get_render_features(features_mv)

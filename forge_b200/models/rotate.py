@@ -100,6 +100,39 @@ class Rotate_world(nn.Module):
         pose_1 = camPoses_cv2[:, 1:].reshape(B * (t - 1), 4, 4)
         return pose_0 @ torch.inverse(pose_1)
 
+    def _jobs_aliased(self, B, t, device, order):
+        """resample jobs only (no view-0 copy): view v >= 1 of object b lands in slot (position of v in order[b]) - 1 of a
+        [B, t-1] output; order[b, 0] must be 0"""
+        src = (torch.arange(B, device=device).view(B, 1) * t + torch.arange(1, t, device=device).view(1, t - 1))
+        if order is None:
+            slot = torch.arange(t - 1, device=device).view(1, t - 1).expand(B, t - 1)
+        else:
+            slot = torch.argsort(order.to(device), dim=1)[:, 1:] - 1
+        dst = slot + torch.arange(B, device=device).view(B, 1) * (t - 1)
+        return torch.stack([src.reshape(-1), dst.reshape(-1), torch.zeros(B * (t - 1), dtype=torch.long, device=device)],
+                           dim=1).int().contiguous()
+
+    def forward_views(self, voxels, camPoses_cv2, grid_size=32, order=None):
+        """Same resample as ``forward`` but WITHOUT the view-0 passthrough copy (reference :141 materialises it with
+        torch.cat): returns a list of t tensors [B,C,D,H,W] (channels-last memory) -- slot 0 is view 0 of the input itself
+        (zero-copy when the input is channels-last), slots 1.. are views of one [B, t-1, D, H, W, C] resample output.
+        ``order`` as in forward; its first column must be 0 (view 0 is the nearest view to itself)."""
+        if not voxels.is_cuda:
+            raise RuntimeError("forge_b200.Rotate_world needs CUDA voxels; there is no CPU path")
+        B, t, C, D, H, W = voxels.shape
+        device = voxels.device
+        gx, gy, gz, gmax = self._device_axes(D, H, W, device)
+        if grid_size != D:
+            gmax = self._compute_axis(grid_size)[1]
+        A = ops.pose_affine(camPoses_cv2.to(device))
+        vox_cl = ops.to_channels_last(voxels.reshape(B * t, C, D, H, W))
+        views = [vox_cl.view(B, t, D, H, W, C)[:, 0].permute(0, 4, 1, 2, 3)]
+        if t > 1:
+            out_cl = ops.rotate_resample(vox_cl, A, self._jobs_aliased(B, t, device, order), gx, gy, gz, gmax, B * (t - 1))
+            out = out_cl.view(B, t - 1, D, H, W, C).permute(0, 1, 5, 2, 3, 4)
+            views += [out[:, i] for i in range(t - 1)]
+        return views
+
     def forward(self, voxels, camPoses_cv2, grid_size=32, order=None):
         '''
         voxels: [B,t,C,D,H,W] features of all frames; camPoses_cv2: [B,t,4,4] camera-to-world poses.
