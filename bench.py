@@ -232,7 +232,7 @@ def k2_setup(cfg, objects, views, C, n, seed, dev):
     vcl = vox.permute(0, 1, 3, 4, 5, 2).contiguous().reshape(objects * views, n, n, n, C)
     del vox
     gx, gy, gz, gmax = rot._device_axes(n, n, n, dev)
-    A = ops.pose_affine(poses)
+    A = ops.pose_affine(poses).view(objects, views, 12)[:, 1:].reshape(-1, 12).contiguous()      # one affine per job
     # transform jobs only: the pipeline aliases view 0 of the input instead of copying it (Rotate_world.forward_views)
     jobs = rot._jobs_aliased(objects, views, dev, None)
     out = torch.empty(objects * (views - 1), n, n, n, C, device=dev)

@@ -128,6 +128,7 @@ class Rotate_world(nn.Module):
         vox_cl = ops.to_channels_last(voxels.reshape(B * t, C, D, H, W))
         views = [vox_cl.view(B, t, D, H, W, C)[:, 0].permute(0, 4, 1, 2, 3)]
         if t > 1:
+            A = A.view(B, t, 12)[:, 1:].reshape(B * (t - 1), 12)          # one affine per JOB (the kernel's contract)
             out_cl = ops.rotate_resample(vox_cl, A, self._jobs_aliased(B, t, device, order), gx, gy, gz, gmax, B * (t - 1))
             out = out_cl.view(B, t - 1, D, H, W, C).permute(0, 1, 5, 2, 3, 4)
             views += [out[:, i] for i in range(t - 1)]
