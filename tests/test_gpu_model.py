@@ -128,3 +128,50 @@ def test_pose_gradient_is_unchanged_by_prepare_for_pose_refinement():
     assert g0.abs().max().item() > 0
     assert abs(l0 - l1) <= 1e-5 * max(1.0, abs(l0))
     assert (g0 - g1).abs().max().item() <= 2e-3 * g0.abs().max().item()
+
+
+def test_graphed_refine_iteration_matches_eager_loop():
+    """forward + loss + backward + Adam step replayed as one CUDA graph (forge_b200.refine.GraphedPoseRefiner) against the
+    same iteration run eagerly for 20 steps (reference kubric_eval.py:450-504).  Atomic reductions in the backward kernels
+    reorder fp32 sums from run to run, so the comparison is to fp32 noise, not bit for bit."""
+    import copy
+    from forge_b200.refine import prepare_for_pose_refinement, make_refine_loss, GraphedPoseRefiner
+    from forge_b200.models.model import _mat2quat
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(3)
+    cfg = syn.make_config(img_size=128, n_pts_per_ray=24, use_gt_pose=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = prepare_for_pose_refinement(FORGE(cfg).to(DEV).eval())
+    model.encoder_3d.density_head[6].bias.data.fill_(0.05)
+    sample = syn.kubric_batch(1, n_views_all=5, img_size=128, seed=6)
+    with torch.no_grad():
+        feats = model.lift(sample['images'].to(DEV)).detach()
+    rel = sample['cam_poses_rel_cv2'][0, 1:].to(DEV)
+    q0 = _mat2quat(rel)[:, :4] + torch.tensor([0.0, 0.02, -0.01, 0.03], device=DEV)
+    t0 = rel[:, :3, 3] + 0.01
+    tgt = torch.rand(5, 3, 128, 128, device=DEV)
+    tgt_m = (torch.rand(5, 1, 128, 128, device=DEV) > 0.5).float()
+    loss_fn = make_refine_loss(model, feats, sample['K_cv2'].to(DEV), sample['cam_poses_cv2_canonicalized'][0, 0], tgt, tgt_m)
+
+    # eager loop
+    q, t = q0.clone().requires_grad_(True), t0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([{'params': [q], 'lr': 1e-3}, {'params': [t], 'lr': 5e-4}], lr=1e-3)
+    losses = []
+    for _ in range(20):
+        opt.zero_grad()
+        loss = loss_fn(q, t)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    # graphed loop
+    r = GraphedPoseRefiner(loss_fn, q0, t0, lr=1e-3, lr_trans=5e-4)
+    for i in range(20):
+        l = r.step()
+        if i in (0, 19):
+            assert abs(l.item() - losses[i]) <= 1e-5 * max(1.0, abs(losses[i]))
+    assert losses[-1] < losses[0]                               # the loop optimises
+    # 20 Adam steps of 1e-3 move a parameter by up to 2e-2; Adam's normalisation amplifies gradient noise on near-zero components
+    assert (r.quat - q).abs().max().item() <= 1e-3 and (r.trans - t).abs().max().item() <= 1e-3
+    assert (r.quat - q0).abs().max().item() > 1e-3              # and the parameters did move

@@ -141,6 +141,21 @@ def main():
         ms = (time.perf_counter() - t0) / args.iters * 1e3
         results[name] = {"ms_per_iteration": round(ms, 3), "final_loss": round(loss.item(), 6),
                          "grad_q_norm": float("%.4e" % q.grad.norm().item()), "grad_t_norm": float("%.4e" % t.grad.norm().item())}
+    # ---- the same iteration replayed as one CUDA graph (forge_b200.refine.GraphedPoseRefiner) ----
+    from forge_b200.refine import GraphedPoseRefiner, make_refine_loss
+    if not args.only or "graph" in args.only:
+        for name, bf in (("graphed iteration, frozen weights, fp32", None), ("graphed iteration, frozen weights, bf16 fusion+heads, tensor-core decoder", torch.bfloat16)):
+            prepare_for_pose_refinement(model, fusion_dtype=bf, decoder_dtype=bf)
+            loss_fn = make_refine_loss(model, features, sample['K_cv2'].to(DEV), canon_pose, target_rgb, target_mask)
+            q, t = make_params()
+            r = GraphedPoseRefiner(loss_fn, q.detach(), t.detach(), lr=1e-3)
+            r.step(3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r.step(args.iters)
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) / args.iters * 1e3
+            results[name] = {"ms_per_iteration": round(ms, 3), "final_loss": round(r.loss.item(), 6)}
     print(json.dumps({"bench": "test-time pose optimisation iteration (b=1, t=5, 64^3, 5x128^2x64)", **results}))
 
 
