@@ -57,6 +57,7 @@ struct Params {
     float* out_f32;                // PLAIN: y fp32 (nullable); GATE: u; OUT: h'
     __nv_bfloat16* out_bf16;       // PLAIN: y bf16 (nullable); GATE: h * r; OUT: h' bf16 (nullable)
     float* out_norm;               // OUT: fusion_norm(h') (nullable)
+    float* aux;                    // GATE: reset gate r; OUT: candidate c = tanh(.) (nullable; saved for the backward pass)
 };
 
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
@@ -247,6 +248,11 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     } else {                    // reset gate r -> h * r as the bf16 operand of the out-gate convolution
                         const float4* hp = reinterpret_cast<const float4*>(p.h + vox * Cg + (c0 - Cg));
                         uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + vox * Cg + (c0 - Cg));
+                        if (p.aux) {
+                            float4* ra = reinterpret_cast<float4*>(p.aux + vox * Cg + (c0 - Cg));
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) ra[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                        }
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float4 h0 = __ldg(hp + 2 * e), h1 = __ldg(hp + 2 * e + 1);
@@ -258,15 +264,18 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 } else {
                     const float4* hp = reinterpret_cast<const float4*>(p.h + vox * Cg + c0);
                     const float4* up = reinterpret_cast<const float4*>(p.u_in + vox * Cg + c0);
+                    float4* ca = p.aux ? reinterpret_cast<float4*>(p.aux + vox * Cg + c0) : nullptr;
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const float4 h4 = __ldg(hp + e), u4 = __ldg(up + e);
                         const float hh[4] = {h4.x, h4.y, h4.z, h4.w}, uu[4] = {u4.x, u4.y, u4.z, u4.w};
+                        float cc[4];
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
-                            const float cnd = tanhf(v[4 * e + t] + __ldg(p.shift + c0 + 4 * e + t));
-                            v[4 * e + t] = hh[t] * (1.f - uu[t]) + cnd * uu[t];        // reference fusion.py:35
+                            cc[t] = tanhf(v[4 * e + t] + __ldg(p.shift + c0 + 4 * e + t));
+                            v[4 * e + t] = hh[t] * (1.f - uu[t]) + cc[t] * uu[t];        // reference fusion.py:35
                         }
+                        if (ca) ca[e] = make_float4(cc[0], cc[1], cc[2], cc[3]);
                     }
                     float4* o = reinterpret_cast<float4*>(p.out_f32 + vox * Cg + c0);
 #pragma unroll
@@ -318,7 +327,7 @@ static int act_map(const char* fn, CUtensorMap* m, const void* ptr, long long ba
 extern "C" int forge_conv3d_tc(const void* x, long long x_batch_stride, int Cx, const void* h2, long long h_batch_stride,
                                int Ch, const void* wpack, int mode, int lrelu, const float* scale, const float* shift,
                                const float* norm_shift, const float* h_state, const float* u_in, float* out_f32,
-                               void* out_bf16, float* out_norm, int B, int D, int H, int W, int Cout, int max_ctas,
+                               void* out_bf16, float* out_norm, float* aux, int B, int D, int H, int W, int Cout, int max_ctas,
                                void* stream) {
     FORGE_RANGE("forge_conv3d_tc");
     using namespace forge;
@@ -342,7 +351,7 @@ extern "C" int forge_conv3d_tc(const void* x, long long x_batch_stride, int Cx, 
     p.nchunk_x = Cx / BK, p.nchunk = (Cx + Ch) / BK;
     p.mode = mode, p.lrelu = lrelu;
     p.scale = scale, p.shift = shift, p.norm_shift = norm_shift, p.h = h_state, p.u_in = u_in;
-    p.out_f32 = out_f32, p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16), p.out_norm = out_norm;
+    p.out_f32 = out_f32, p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16), p.out_norm = out_norm, p.aux = aux;
     {   // weights [27 * nchunk][Cout][64] bf16
         const unsigned long long dims[3] = {static_cast<unsigned long long>(BK), static_cast<unsigned long long>(Cout),
                                             static_cast<unsigned long long>(27 * p.nchunk)};

@@ -55,9 +55,9 @@ class ConvGRU_3D(nn.Module):
         views = list(x) if isinstance(x, (list, tuple)) else None
         x0 = views[0] if views else x[:, 0]
         b, c, d, h, w = x0.shape
-        needs_graph = torch.is_grad_enabled() and (any(v.requires_grad for v in (views or [x])) or
-                                                    any(p.requires_grad for p in self.parameters()))
-        return (x0.is_cuda and not self.training and not needs_graph and self.n_layers == 1 and c % 64 == 0 and self.hidden_size == 128
+        # weight gradients need the cuDNN path; a graph to the views only (pose refinement) is served by ops.gru_tc
+        needs_wgrad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        return (x0.is_cuda and not self.training and not needs_wgrad and self.n_layers == 1 and c % 64 == 0 and self.hidden_size == 128
                 and c == self.hidden_size and d % 4 == 0 and h % 4 == 0 and w % 8 == 0)
 
     def _tc_packs(self):
@@ -74,7 +74,11 @@ class ConvGRU_3D(nn.Module):
                 s2, b2 = bn_fold(fc[3], fc[4])
                 ns = (self.fusion_norm.weight / torch.sqrt(self.fusion_norm.running_var + self.fusion_norm.eps)).float().contiguous()
                 nb = (self.fusion_norm.bias - self.fusion_norm.running_mean * ns).float().contiguous()
-                packs = dict(w1=ops.pack_conv3d_weights(fc[0].weight), s1=s1, b1=b1,
+                wg, wo = cell.conv_gate.weight, cell.out_gate.weight
+                packs = dict(wgT=ops.pack_conv3d_weights(wg.transpose(0, 1).flip(2, 3, 4)),        # transposed convolutions
+                             woT=ops.pack_conv3d_weights(wo.transpose(0, 1).flip(2, 3, 4)),        # (backward w.r.t. the input)
+                             zero256=torch.zeros(256, dtype=torch.float32, device=wg.device),
+                             w1=ops.pack_conv3d_weights(fc[0].weight), s1=s1, b1=b1,
                              w2=ops.pack_conv3d_weights(fc[3].weight), s2=s2, b2=b2,
                              wg=ops.pack_conv3d_weights(cell.conv_gate.weight), bg=cell.conv_gate.bias.float().contiguous(),
                              wo=ops.pack_conv3d_weights(cell.out_gate.weight), bo=cell.out_gate.bias.float().contiguous(),
@@ -89,6 +93,15 @@ class ConvGRU_3D(nn.Module):
         pk = self._tc_packs()
         views = list(x) if isinstance(x, (list, tuple)) else list(x.unbind(dim=1))
         t = len(views)
+        if torch.is_grad_enabled() and any(v.requires_grad for v in views):
+            # a graph to the views is wanted (weights are constants): h0 through the module's own convolutions (autograd),
+            # the recurrence through the differentiable tensor-core op
+            mean = views[0]
+            for v in views[1:]:
+                mean = mean + v
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                h0 = self.fusion_conv(mean / t)
+            return ops.gru_tc(pk, h0.float(), views)
         xb = [v.to(torch.bfloat16) for v in views]                 # .to keeps K2's channels-last memory order
         xm = views[0].float()
         for v in views[1:]:

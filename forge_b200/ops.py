@@ -667,7 +667,7 @@ def _bf16_cl(t):
 
 
 def conv3d_tc(x, wpack, mode, shift, h2=None, scale=None, lrelu=False, norm_shift=None, h_state=None, u_in=None,
-              want_f32=True, want_bf16=False, want_norm=False, max_ctas=0):
+              want_f32=True, want_bf16=False, want_norm=False, want_aux=False, max_ctas=0):
     """forge_conv3d_tc on [B,C,D,H,W] tensors (channels-last memory).  Returns (out_f32, out_bf16, out_norm) as
     [B,Cg,D,H,W] channels-last views (None where not requested).  mode: 'plain' | 'gate' | 'out' (see forge_b200.h)."""
     _require_cuda(x, wpack, shift)
@@ -694,9 +694,76 @@ def conv3d_tc(x, wpack, mode, shift, h2=None, scale=None, lrelu=False, norm_shif
     o32 = cl(torch.float32) if (want_f32 or m != 0) else None
     o16 = cl(torch.bfloat16) if (want_bf16 or m == 1) else None
     on = cl(torch.float32) if want_norm else None
+    ax = cl(torch.float32) if want_aux else None
     with torch.cuda.device(dev):
         _lib.call("forge_conv3d_tc", _ptr(xb), xbs, Cx, _ptr(hb), hbs, Ch, _ptr(wpack), m, int(bool(lrelu)), _ptr(scale),
-                  _ptr(shift), _ptr(norm_shift), _ptr(hs), _ptr(ui), _ptr(o32), _ptr(o16), _ptr(on), B, D, H, W, Cout,
+                  _ptr(shift), _ptr(norm_shift), _ptr(hs), _ptr(ui), _ptr(o32), _ptr(o16), _ptr(on), _ptr(ax), B, D, H, W, Cout,
                   int(max_ctas), _stream(x))
     view = lambda t: None if t is None else t.permute(0, 4, 1, 2, 3)     # noqa: E731
+    if want_aux:
+        return view(o32), view(o16), view(on), view(ax)
     return view(o32), view(o16), view(on)
+
+
+class _GruTC(torch.autograd.Function):
+    """The ConvGRU recurrence over the views + fusion_norm (eval) on forge_conv3d_tc, differentiable w.r.t. the views and the
+    initial state (constant weights: the pose-refinement loop).  Backward = the two transposed convolutions per step through the
+    same kernel (flipped / transposed weight packs) + the gate derivatives."""
+
+    @staticmethod
+    def forward(ctx, pk, h0, *views):
+        t = len(views)
+        xb = [v.to(torch.bfloat16) for v in views]
+        h = h0.float()
+        h16 = h.to(torch.bfloat16)
+        saved = []
+        out = None
+        for i in range(t):
+            last = i == t - 1
+            u, hr, _, r = conv3d_tc(xb[i], pk['wg'], 'gate', pk['bg'], h2=h16, h_state=h, want_aux=True)
+            hn, hn16, out, c = conv3d_tc(xb[i], pk['wo'], 'out', pk['bo'], h2=hr, h_state=h, u_in=u, scale=pk['ns'],
+                                         norm_shift=pk['nb'], want_bf16=not last, want_norm=last, want_aux=True)
+            saved += [h, u, r, c]
+            h, h16 = hn, hn16
+        ctx.pk, ctx.t = pk, t
+        ctx.save_for_backward(*saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        pk, t = ctx.pk, ctx.t
+        saved = ctx.saved_tensors
+        B, C, D, H, W = saved[0].shape
+        N, dev = B * D * H * W, d_out.device
+        zero = pk['zero256']
+        st = _stream(d_out)
+
+        def rows(x):                  # [B,C,D,H,W] -> dense channels-last rows [N, C] fp32 (zero-copy for the saved tensors)
+            x = x.permute(0, 2, 3, 4, 1)
+            return x if (x.is_contiguous() and x.dtype == torch.float32) else x.float().contiguous()
+
+        def new(c, dtype=torch.float32):
+            return torch.empty(B, D, H, W, c, dtype=dtype, device=dev)
+
+        dh = rows(d_out * pk['ns'].view(1, -1, 1, 1, 1))                  # through fusion_norm (eval): a per-channel scale
+        dxs = [None] * t
+        with torch.cuda.device(dev):
+            for i in reversed(range(t)):
+                h, u, r, c = (rows(x) for x in saved[4 * i:4 * i + 4])
+                d_o, dgu, dh_dir = new(C, torch.bfloat16), new(C), new(C)
+                _lib.call("forge_gru_tc_bwd", 0, _ptr(dh), _ptr(u), _ptr(c), _ptr(h), None, _ptr(d_o), _ptr(dgu), _ptr(dh_dir), N, C, st)
+                g1, _, _ = conv3d_tc(d_o.permute(0, 4, 1, 2, 3), pk['woT'], 'plain', zero)      # [dx_o | d(h r)]
+                g1 = rows(g1)
+                dg, dh_acc = new(2 * C, torch.bfloat16), new(C)
+                _lib.call("forge_gru_tc_bwd", 1, _ptr(g1), _ptr(r), _ptr(h), _ptr(dgu), _ptr(dh_dir), _ptr(dg), _ptr(dh_acc), None, N, C, st)
+                g2, _, _ = conv3d_tc(dg.permute(0, 4, 1, 2, 3), pk['wgT'], 'plain', zero)       # [dx_g | dh_g]
+                g2 = rows(g2)
+                dx, dh = new(C), new(C)
+                _lib.call("forge_gru_tc_bwd", 2, _ptr(g1), _ptr(g2), _ptr(dh_acc), None, None, None, _ptr(dx), _ptr(dh), N, C, st)
+                dxs[i] = dx.permute(0, 4, 1, 2, 3)
+        return (None, dh.permute(0, 4, 1, 2, 3), *dxs)
+
+
+def gru_tc(pk, h0, views):
+    """fusion_norm(GRU(views; h0)) on the tensor cores with autograd support for views / h0 (weights are constants)."""
+    return _GruTC.apply(pk, h0, *views)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 14
+#define FORGE_ABI_VERSION 16
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -246,11 +246,21 @@ int forge_sample_points(const float* pts, int M, int D, int H, int W, int align_
  *                   out_bf16 = h_state * r [..][C]           (h_state fp32 [B][D][H][W][C])
  *   mode 2 (out):   Cout = C; c = tanh(acc + shift); h' = h_state (1 - u_in) + c u_in; out_f32 = h', out_bf16 = h' (nullable),
  *                   out_norm = h' * scale + norm_shift (nullable; fusion_norm in eval mode)
+ *   aux (nullable, fp32 [..][C]): gate mode stores r, out mode stores c -- what the backward pass of the cell needs
  *   max_ctas: 0 = one persistent CTA per SM */
 int forge_conv3d_tc(const void* x, long long x_batch_stride, int Cx, const void* h2, long long h_batch_stride, int Ch,
                     const void* wpack, int mode, int lrelu, const float* scale, const float* shift,
                     const float* norm_shift, const float* h_state, const float* u_in, float* out_f32, void* out_bf16,
-                    float* out_norm, int B, int D, int H, int W, int Cout, int max_ctas, void* stream);
+                    float* out_norm, float* aux, int B, int D, int H, int W, int Cout, int max_ctas, void* stream);
+
+/* Elementwise stages of the backward pass of the tensor-core ConvGRU cell (constant weights), dense channels-last rows
+ * [N = B D H W][C] fp32 unless noted; between them run the two transposed convolutions (forge_conv3d_tc, plain mode):
+ *   stage 0: a0 dh', a1 u, a2 c, a3 h                       -> o_bf16 d_o [N][C], o0 dgu, o1 dh_dir
+ *   stage 1: a0 g1 [N][2C] = [dx_o | d(h r)], a1 r, a2 h, a3 dgu, a4 dh_dir -> o_bf16 dg [N][2C], o0 dh_acc
+ *   stage 2: a0 g1 [N][2C], a1 g2 [N][2C] = [dx_g | dh_g], a2 dh_acc        -> o0 dx, o1 dh
+ * (derivation: reference models/fusion.py:29-35) */
+int forge_gru_tc_bwd(int stage, const float* a0, const float* a1, const float* a2, const float* a3, const float* a4,
+                     void* o_bf16, float* o0, float* o1, long long N, int C, void* stream);
 
 #ifdef __cplusplus
 }
