@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
     import bench
     # each rank "measures" a different time; the job-level figure is total rays / max time
     my_ms = 10.0 * (rank + 1)
-    total_ms, e2e_ms, k1 = bench.reduce_times(my_ms, 2 * my_ms, 0.5 * my_ms, world, torch.device("cpu"))
+    total_ms, e2e_ms, k1 = bench.reduce_max([my_ms, 2 * my_ms, 0.5 * my_ms], world, torch.device("cpu"))
     lo, hi = shard_objects(9, rank, world)
     n = torch.tensor([hi - lo])
     dist.all_reduce(n)
