@@ -67,30 +67,34 @@ def main():
     out["forge_b200 fp32 ms"] = round(timed(fwd, args.iters), 3)
 
     # ---- stage breakdown of the same forward ----
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-    with torch.no_grad():
-        clips = sample['images'][:, :5]
-        ev[0].record()
-        feats = model.lift(clips)
-        ev[1].record()
-        P = sample['cam_poses_cv2_canonicalized'][:, :5]
-        idxs = sequence_from_distance(P[:, :, :3, 3])
-        rot = model.rotate(voxels=feats, camPoses_cv2=P, grid_size=feats.shape[3], order=idxs)
-        ev[2].record()
-        fmv = model.encoder_3d.fuse(rot)
-        ev[3].record()
-        dens = model.encoder_3d.get_density3D(fmv)
-        feat = model.encoder_3d.get_render_features(fmv)
-        ev[4].record()
-        E = sample['cam_extrinsics_cv2_canonicalized'].reshape(b * t_all, 4, 4)
-        cam = {'R': E[:, :3, :3], 'T': E[:, :3, 3], 'K': sample['K_cv2'].reshape(b * t_all, 3, 3).clone()}
-        v2v = torch.arange(b, device=DEV).repeat_interleave(t_all).int()
-        model.render(cam, feat, dens, return_origin_proj=True, view2vol=v2v)
-        ev[5].record()
-        torch.cuda.synchronize()
-    names = ["lift (ResNet50 + 3-D conv, cuDNN)", "sort + rotate (K2)", "fuse (ConvGRU, cuDNN)", "heads (cuDNN)",
-             "render (camera prep + pack + K1 + decoder + upsample)"]
-    out["stages_ms"] = {n: round(ev[i].elapsed_time(ev[i + 1]), 3) for i, n in enumerate(names)}
+    def stage_breakdown():
+        from forge_b200.models.model import _view0_first
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        with torch.no_grad():
+            clips = sample['images'][:, :5]
+            ev[0].record()
+            feats = model.lift(clips)
+            ev[1].record()
+            P = sample['cam_poses_cv2_canonicalized'][:, :5]
+            idxs = _view0_first(sequence_from_distance(P[:, :, :3, 3]))
+            rot = model.rotate.forward_views(voxels=feats, camPoses_cv2=P, grid_size=feats.shape[3], order=idxs)
+            ev[2].record()
+            fmv = model.encoder_3d.fuse(rot)
+            ev[3].record()
+            dens = model.encoder_3d.get_density3D(fmv)
+            feat = model.encoder_3d.get_render_features(fmv)
+            ev[4].record()
+            E = sample['cam_extrinsics_cv2_canonicalized'].reshape(b * t_all, 4, 4)
+            cam = {'R': E[:, :3, :3], 'T': E[:, :3, 3], 'K': sample['K_cv2'].reshape(b * t_all, 3, 3).clone()}
+            v2v = torch.arange(b, device=DEV).repeat_interleave(t_all).int()
+            model.render(cam, feat, dens, return_origin_proj=True, view2vol=v2v)
+            ev[5].record()
+            torch.cuda.synchronize()
+        names = ["lift (ResNet50 + 3-D conv, cuDNN)", "sort + rotate (K2)", "fuse (ConvGRU)", "heads (cuDNN)",
+                 "render (camera prep + pack + K1 + decoder + upsample)"]
+        return {n: round(ev[i].elapsed_time(ev[i + 1]), 3) for i, n in enumerate(names)}
+    stage_breakdown()
+    out["stages_ms"] = stage_breakdown()
 
     if not args.no_ref:
         from oracle import reference_path as rp
@@ -131,6 +135,8 @@ def main():
     model.encoder_3d.compute_dtype = torch.bfloat16
     model.render.decoder_dtype = torch.bfloat16
     out["forge_b200 bf16 lift/fusion/heads + tensor-core decoder ms"] = round(timed(fwd, args.iters), 3)
+    stage_breakdown()
+    out["stages_ms bf16 (tensor-core fusion + decoder)"] = stage_breakdown()
     print(json.dumps(out))
 
 
