@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libforge_b200.so")
 STAMP = os.path.join(LIBDIR, "libforge_b200.stamp")
-SOURCES = ["layout.cu", "raymarch.cu", "raymarch_tma.cu", "rotate.cu", "decoder.cu", "decoder_tc.cu", "decoder_bwd.cu", "camera.cu", "gru.cu", "conv3d_tc.cu", "gru_tc_bwd.cu"]
+SOURCES = ["layout.cu", "raymarch.cu", "raymarch_tma.cu", "raymarch_tma1.cu", "rotate.cu", "decoder.cu", "decoder_tc.cu", "decoder_bwd.cu", "camera.cu", "gru.cu", "conv3d_tc.cu", "gru_tc_bwd.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -23,16 +23,9 @@
 // bytes per sample against 512 for the features), software-pipelined one sample ahead.
 #include <cstdlib>
 
-#include "raymarch_common.cuh"
-#include "tensormap.cuh"
+#include "raymarch_tma_common.cuh"
 
 namespace forge {
-
-using namespace async_;
-
-constexpr int kTW = 16;                           // pixel tile of a CTA: 16 x (4 kWarpsY); 4 kWarpsY consumer warps + 1 producer
-constexpr int kSlabMax = 8;                       // most samples per slab
-constexpr int kMaxStages = 4;
 
 // Static in-plane box shapes of the tensor maps (voxels in x, y): a slab's brick is fetched as ez z-planes of the smallest
 // shape that covers its footprint, one cp.async.bulk.tensor (UTMALDG) per plane.  (Row-wise cp.async.bulk copies, ~53 per
@@ -45,68 +38,6 @@ constexpr int kBoxY[kNumBY] = {6, 8, 12, 16};
 struct TmaMaps {
     CUtensorMap m[kNumBX * kNumBY];      // index = iy * kNumBX + ix
 };
-
-struct SlabHeader {
-    int ka, kb;          // sample range [ka, kb)
-    int lx, ly, lz;      // box origin in padded voxel coordinates
-    int ex, ey, ez;      // box extent = pitches of the brick (0 = nothing resident)
-    int shape;           // tensor-map index
-};
-
-struct TmaSmem {
-    unsigned long long full[kMaxStages], empty[kMaxStages];
-    SlabHeader hdr[8];                   // slab s lives in hdr[s & 7] (planned up to kStages + 1 slabs ahead)
-    float cam[12];
-    int kt0, kt1;
-    float zs[kMaxP];
-};
-constexpr int tma_smem_bytes(int stages, int stage_vox) { return stages * stage_vox * 64 + static_cast<int>(sizeof(TmaSmem)); }
-
-struct Box {
-    int lo[3], ex[3];
-    __device__ __forceinline__ int vol() const { return ex[0] * ex[1] * ex[2]; }
-};
-
-// Box (padded voxel coordinates, clipped to the padded volume) of all corner footprints of the samples k in [ka, kb) of
-// the tile's rays: positions are multilinear in (pixel, depth), so the 4 corner rays at the 2 end depths bound them.
-__device__ __forceinline__ Box slab_box(const float* cam, const float* zs, int ka, int kb, float u0, float u1, float v0,
-                                        float v1, int D, int H, int W) {
-    const float za = zs[ka], zb = zs[kb - 1];
-    const int size[3] = {W, H, D};
-    Box b;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float m0 = cam[3 + 3 * a], m1 = cam[4 + 3 * a], m2 = cam[5 + 3 * a], o = cam[a];
-        float lo = 3.0e38f, hi = -3.0e38f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float d = fmaf(m0, (c & 1) ? u1 : u0, fmaf(m1, (c & 2) ? v1 : v0, m2));
-            const float pa = fmaf(za, d, o), pb = fmaf(zb, d, o);
-            lo = fminf(lo, fminf(pa, pb));
-            hi = fmaxf(hi, fmaxf(pa, pb));
-        }
-        // padded voxel coordinate = (p + 1) / 2 * (size - 1) + 1; base = floor, upper corner = base + 1
-        const float s = 0.5f * static_cast<float>(size[a] - 1);
-        lo = fmaxf(fminf((lo + 1.f) * s + 1.f - 1e-3f, 3.0e4f), -3.0e4f);
-        hi = fmaxf(fminf((hi + 1.f) * s + 1.f + 1e-3f, 3.0e4f), -3.0e4f);
-        int l = static_cast<int>(floorf(lo)), h = static_cast<int>(floorf(hi)) + 1;
-        l = max(l, 0);
-        h = min(h, size[a] + 1);
-        b.lo[a] = l;
-        b.ex[a] = max(h - l + 1, 0);
-    }
-    if (b.ex[0] == 0 || b.ex[1] == 0 || b.ex[2] == 0) b.ex[0] = b.ex[1] = b.ex[2] = 0;
-    return b;
-}
-
-__device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-__device__ __forceinline__ void fma4(float* acc, float w, const float4 v) {
-    const float2 w2 = make_float2(w, w);
-    float2 a = __ffma2_rn(make_float2(v.x, v.y), w2, make_float2(acc[0], acc[1]));
-    float2 b = __ffma2_rn(make_float2(v.z, v.w), w2, make_float2(acc[2], acc[3]));
-    acc[0] = a.x, acc[1] = a.y, acc[2] = b.x, acc[3] = b.y;
-}
 
 // kStages x kStageVox voxels (64 B each) of brick ring per CTA; two CTAs per SM
 template <int kStages, int kStageVox, int kWarpsY>
@@ -199,7 +130,9 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
         for (int e = 0; e < kNumBY - 1; ++e) iy += (mine.ex[1] > c_box_y[e]);
         const int bx = c_box_x[ix], by = c_box_y[iy];
         const bool empty = mine.ex[0] == 0;
-        const unsigned fits = __ballot_sync(0xffffffffu, empty || bx * by * mine.ex[2] <= kStageVox) & ((1u << kSlabMax) - 1u);
+        // a candidate fits when its footprint is covered by the largest shape AND the brick fits the stage
+        const bool covered = mine.ex[0] <= c_box_x[kNumBX - 1] && mine.ex[1] <= c_box_y[kNumBY - 1];
+        const unsigned fits = __ballot_sync(0xffffffffu, empty || (covered && bx * by * mine.ex[2] <= kStageVox)) & ((1u << kSlabMax) - 1u);
         const int pick = max(__ffs(~fits) - 1, 1) - 1;      // longest run of fitting candidates, at least one sample
         if (lane == pick) {
             SlabHeader h;
@@ -359,6 +292,10 @@ static int tma_launch_cfg(const char* fn, const TmaMaps& maps, const float* feat
     return check_launch(fn);
 }
 
+int raymarch_fwd_tma1_launch(const char* fn, const float* feat_pad, const float4* dens_quad, const int* view2vol,
+                             const float* cam12, const float* zs, float* out_feat, float* out_sil, float* out_depth, int N,
+                             int V, int D, int H, int W, int S_h, int S_w, int P, cudaStream_t st);      // raymarch_tma1.cu
+
 int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4* dens_quad, const int* view2vol,
                             const float* cam12, const float* zs, float* out_feat, float* out_sil, float* out_depth, int N,
                             int V, int D, int H, int W, int S_h, int S_w, int P, cudaStream_t st) {
@@ -366,6 +303,9 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
         const char* e = getenv("FORGE_K1T_RING");
         return e ? atoi(e) : 2;
     }();
+    if (ring == 7)          // one lane per ray (raymarch_tma1.cu)
+        return raymarch_fwd_tma1_launch(fn, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D, H, W, S_h,
+                                        S_w, P, st);
     // tensor maps over feat_pad viewed as [V (D+2)] [H+2] [W+2] [16] fp32, one per static in-plane box shape (host-side
     // encode, ~1 us each; passed to the kernel as __grid_constant__ parameters: no device allocation)
     alignas(64) TmaMaps maps;
