@@ -42,6 +42,29 @@ class Encoder3D(nn.Module):
         self.tc_fusion = True
         self._trunk_channels_last = False
 
+    def _conv1_tc_eligible(self, z_3d):
+        """the lifting convolution (64 -> 128, BN, LeakyReLU; reference :36-40, :50) on forge_conv3d_tc: bf16 mode, eval-mode BN,
+        no autograd graph wanted, a grid the kernel tiles"""
+        _, _, D, H, W = z_3d.shape
+        wants_graph = torch.is_grad_enabled() and (z_3d.requires_grad or any(p.requires_grad for p in self.conv1.parameters()))
+        return (self.compute_dtype == torch.bfloat16 and self.tc_fusion and z_3d.is_cuda and not self.conv1.training
+                and not wants_graph and D % 4 == 0 and H % 4 == 0 and W % 8 == 0)
+
+    def _conv1_tc(self, z_3d):
+        from .. import ops
+        conv, bn = self.conv1[0], self.conv1[1]
+        tensors = list(self.conv1.parameters()) + list(self.conv1.buffers())
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if getattr(self, '_conv1_pack', None) is None or self._conv1_pack[0] != key:
+            with torch.no_grad():
+                s = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+                b = ((conv.bias - bn.running_mean) * s + bn.bias).float().contiguous()
+                self._conv1_pack = (key, ops.pack_conv3d_weights(conv.weight), s, b)
+        _, w, s, b = self._conv1_pack
+        x = z_3d.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)      # one re-layout pass of the lifted volume
+        y, _, _ = ops.conv3d_tc(x, w, 'plain', b, scale=s, lrelu=True)
+        return y                                          # fp32, channels-last memory: what K2 consumes zero-copy
+
     def get_feat3D(self, img):
         with self._amp():
             if self._trunk_channels_last:
@@ -50,6 +73,8 @@ class Encoder3D(nn.Module):
             B, C, H, W = z_2d.shape                   # stride-8 feature map
             # the lift is a reshape of the NCHW tensor: 2048 = 64 ch x 32 depth (needs NCHW memory order)
             z_3d = z_2d.contiguous().view(-1, 64, 32, H, W)
+            if self._conv1_tc_eligible(z_3d):
+                return self._conv1_tc(z_3d)
             if self._trunk_channels_last:
                 z_3d = z_3d.contiguous(memory_format=torch.channels_last_3d)
             return self.conv1(z_3d).float()

@@ -133,3 +133,23 @@ def test_fuse_on_tensor_cores_matches_reference_within_bf16_tolerance():
     # with a graph wanted the module falls back to autograd-capable convolutions
     v2 = views.clone().requires_grad_(True)
     assert not m.fusion_feature.tc_eligible(v2)
+
+
+def test_lift_convolution_on_tensor_cores_matches_reference_within_bf16_tolerance():
+    """Encoder3D.get_feat3D with the 64 -> 128 lifting convolution on forge_conv3d_tc (BN folded, LeakyReLU fused) and the
+    ResNet trunk under bf16 autocast, against the fp32 reference fixture"""
+    g = load_golden("encoder_small")
+    s = g['seed']
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = seeded.load_seeded(Encoder3D(syn.make_config()), s).to(DEV).eval()
+    m.channels_last_3d_()
+    m.compute_dtype = torch.bfloat16
+    img = seeded.seeded_tensor(s, 'img', (1, 3, 64, 64), kind='rand').to(DEV)          # 64^2 image -> 8 x 8 feature map (W % 8 == 0)
+    with torch.no_grad():
+        z = m.feature_extraction(img.contiguous(memory_format=torch.channels_last)).float().contiguous().view(-1, 64, 32, 8, 8)
+        assert m._conv1_tc_eligible(z)
+        got = m._conv1_tc(z)
+        ref = m.conv1(z)                        # fp32 cuDNN on the same trunk output
+    assert got.shape == ref.shape
+    assert _err(got, ref) <= 2e-2
