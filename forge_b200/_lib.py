@@ -44,11 +44,12 @@ _SIGNATURES = {
     "forge_gru_gate_bwd": (_c.c_int, [_F, _F, _I, _F, _c.c_longlong, _F, _F, _F, _I, _I, _I, _I, _F]),
     "forge_gru_out_fwd": (_c.c_int, [_F, _F, _I, _F, _c.c_longlong, _F, _I, _I, _I, _I, _F]),
     "forge_gru_out_bwd": (_c.c_int, [_F, _F, _F, _I, _F, _c.c_longlong, _F, _F, _F, _I, _I, _I, _I, _F]),
-    "forge_conv3d_tc": (_c.c_int, [_F, _c.c_longlong, _I, _F, _c.c_longlong, _I, _F, _I, _I] + [_F] * 9 + [_I] * 6 + [_F]),
+    "forge_conv3d_tc": (_c.c_int, [_F, _c.c_longlong, _I, _F, _c.c_longlong, _I, _F, _I, _I] + [_F] * 9 + [_I] * 8 + [_F]),
+    "forge_conv3d_c8_to_1_relu": (_c.c_int, [_F, _F, _c.c_float, _F, _I, _I, _I, _I, _F]),
     "forge_gru_tc_bwd": (_c.c_int, [_I] + [_F] * 8 + [_c.c_longlong, _I, _F]),
     "forge_sample_points": (_c.c_int, [_F, _I, _I, _I, _I, _I, _F, _F, _F]),
 }
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 _lock = threading.Lock()
 _lib = None

@@ -40,14 +40,15 @@ template <int BN>
 struct Cfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int SMEM = STAGES * STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
 };
 
 struct Params {
     int B, D, H, W, Cout;
     int nchunk_x, nchunk;          // 64-channel chunks of the first source / of both sources
-    int mode;                      // 0 PLAIN, 1 GATE, 2 OUT
+    int mode;                      // 0 PLAIN, 1 GATE, 2 OUT, 3 SHUFFLE (x2 pixel shuffle of 8 x 32 columns), 4 HEADS (split outputs)
+    int out_pitch, out_off;        // SHUFFLE: channels per output voxel row / first channel written; HEADS: split column
     int lrelu;                     // PLAIN: apply LeakyReLU(0.01)
     const float* scale;            // PLAIN: per-channel scale (nullable = 1); OUT: fusion_norm scale (nullable = no norm output)
     const float* shift;            // PLAIN: per-channel shift (bias folded in); GATE / OUT: conv bias; OUT: see norm_shift
@@ -261,6 +262,37 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                                               pack_bf16(h1.z * v[8 * e + 6], h1.w * v[8 * e + 7]));
                         }
                     }
+                } else if (p.mode == 3) {
+                    // transposed convolution (k 4, stride 2, pad 1) as a 27-tap GEMM whose 8 column groups of 32 are the 8
+                    // output parity classes: columns [32 q, 32 q + 32) of input voxel (z, y, x) are the 32 channels of output
+                    // voxel (2z + qz, 2y + qy, 2x + qx); BN + LeakyReLU folded, stored bf16 at channel offset out_off of rows
+                    // of out_pitch channels
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float t = v[e] * __ldg(p.scale + c0 + e) + __ldg(p.shift + c0 + e);
+                        v[e] = p.lrelu ? fmaxf(t, 0.01f * t) : t;
+                    }
+                    const int q = c0 >> 5;
+                    const long long ovox = ((static_cast<long long>(n) * (2 * p.D) + (2 * z + (q >> 2))) * (2 * p.H) + (2 * y + ((q >> 1) & 1))) *
+                                               (2 * p.W) + (2 * x + (q & 1));
+                    uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + ovox * p.out_pitch + p.out_off);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        o[e] = make_uint4(pack_bf16(v[8 * e], v[8 * e + 1]), pack_bf16(v[8 * e + 2], v[8 * e + 3]),
+                                          pack_bf16(v[8 * e + 4], v[8 * e + 5]), pack_bf16(v[8 * e + 6], v[8 * e + 7]));
+                } else if (p.mode == 4) {
+                    // two heads in one 32-column GEMM: columns [0, 16) -> out_f32 rows of 16 (affine, no activation: the render
+                    // features), columns [16, 24) -> aux rows of 8 (affine + LeakyReLU: the density branch)
+#pragma unroll
+                    for (int e = 0; e < 24; ++e) v[e] = v[e] * __ldg(p.scale + e) + __ldg(p.shift + e);
+                    float4* o = reinterpret_cast<float4*>(p.out_f32 + vox * 16);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                    float4* a = reinterpret_cast<float4*>(p.aux + vox * 8);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        a[e] = make_float4(fmaxf(v[16 + 4 * e], 0.01f * v[16 + 4 * e]), fmaxf(v[17 + 4 * e], 0.01f * v[17 + 4 * e]),
+                                           fmaxf(v[18 + 4 * e], 0.01f * v[18 + 4 * e]), fmaxf(v[19 + 4 * e], 0.01f * v[19 + 4 * e]));
                 } else {
                     const float4* hp = reinterpret_cast<const float4*>(p.h + vox * Cg + c0);
                     const float4* up = reinterpret_cast<const float4*>(p.u_in + vox * Cg + c0);
@@ -312,6 +344,32 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BN) : "memory");
 }
 
+// Conv3d(8 -> 1, 3x3x3, pad 1) + ReLU over channels-last rows of 8 floats: the last layer of the density head (reference
+// models/encoder.py:32-33).  0.45 GFLOP per 64^3 object: one thread per output voxel, 27 x 2 float4 neighbour loads (L1 / L2 hits).
+__global__ void __launch_bounds__(256) conv_c8_to_1_relu_kernel(const float4* __restrict__ x, const float* __restrict__ w,
+                                                                 float bias, float* __restrict__ y, int B, int D, int H, int W) {
+    __shared__ float sw[27 * 8];
+    for (int e = threadIdx.x; e < 27 * 8; e += 256) sw[e] = w[e];
+    __syncthreads();
+    const long long total = static_cast<long long>(B) * D * H * W;
+    for (long long o = blockIdx.x * 256ll + threadIdx.x; o < total; o += static_cast<long long>(gridDim.x) * 256) {
+        const int xw = static_cast<int>(o % W), yh = static_cast<int>((o / W) % H), zd = static_cast<int>((o / (static_cast<long long>(W) * H)) % D);
+        const long long nb = o / (static_cast<long long>(W) * H * D);
+        float acc = bias;
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {
+            const int zz = zd + t / 9 - 1, yy = yh + (t / 3) % 3 - 1, xx = xw + t % 3 - 1;
+            if (zz < 0 || zz >= D || yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const float4* px = x + (((nb * D + zz) * H + yy) * W + xx) * 2;
+            const float4 a = __ldg(px), b = __ldg(px + 1);
+            const float* wt = sw + t * 8;
+            acc = fmaf(a.x, wt[0], fmaf(a.y, wt[1], fmaf(a.z, wt[2], fmaf(a.w, wt[3], acc))));
+            acc = fmaf(b.x, wt[4], fmaf(b.y, wt[5], fmaf(b.z, wt[6], fmaf(b.w, wt[7], acc))));
+        }
+        y[o] = fmaxf(acc, 0.f);
+    }
+}
+
 static int act_map(const char* fn, CUtensorMap* m, const void* ptr, long long batch_stride, int C, int B, int D, int H, int W) {
     const unsigned long long dims[5] = {static_cast<unsigned long long>(C), static_cast<unsigned long long>(W),
                                         static_cast<unsigned long long>(H), static_cast<unsigned long long>(D),
@@ -327,8 +385,8 @@ static int act_map(const char* fn, CUtensorMap* m, const void* ptr, long long ba
 extern "C" int forge_conv3d_tc(const void* x, long long x_batch_stride, int Cx, const void* h2, long long h_batch_stride,
                                int Ch, const void* wpack, int mode, int lrelu, const float* scale, const float* shift,
                                const float* norm_shift, const float* h_state, const float* u_in, float* out_f32,
-                               void* out_bf16, float* out_norm, float* aux, int B, int D, int H, int W, int Cout, int max_ctas,
-                               void* stream) {
+                               void* out_bf16, float* out_norm, float* aux, int out_pitch, int out_off, int B, int D, int H, int W,
+                               int Cout, int max_ctas, void* stream) {
     FORGE_RANGE("forge_conv3d_tc");
     using namespace forge;
     using namespace forge::c3d;
@@ -336,8 +394,12 @@ extern "C" int forge_conv3d_tc(const void* x, long long x_batch_stride, int Cx, 
     if (!x || !wpack || !shift) return fail(fn, "null pointer");
     if (B <= 0 || D % TZ || H % TY || W % TX || D <= 0 || H <= 0 || W <= 0) return fail(fn, "volume sides must be multiples of 4 (z, y) and 8 (x)");
     if (Cx <= 0 || Cx % BK || Ch < 0 || Ch % BK || (Ch > 0 && !h2)) return fail(fn, "source channels must be multiples of 64");
-    if (Cout != 128 && Cout != 256) return fail(fn, "Cout must be 128 or 256");
-    if (mode < 0 || mode > 2) return fail(fn, "mode must be 0 (plain), 1 (gate) or 2 (out)");
+    if (Cout != 32 && Cout != 128 && Cout != 256) return fail(fn, "Cout must be 32, 128 or 256");
+    if (mode < 0 || mode > 4) return fail(fn, "mode must be 0 (plain), 1 (gate), 2 (out), 3 (shuffle) or 4 (heads)");
+    if (mode == 3 && (Cout != 256 || !out_bf16 || !scale || out_pitch < 32 || out_off < 0 || out_off + 32 > out_pitch || (out_pitch | out_off) % 8))
+        return fail(fn, "shuffle mode needs Cout = 256 (8 classes x 32), scale, a bf16 output and 8-aligned out_pitch / out_off");
+    if (mode == 4 && (Cout != 32 || !out_f32 || !aux || !scale)) return fail(fn, "heads mode needs Cout = 32, scale, out_f32 [..][16] and aux [..][8]");
+    if (mode != 4 && mode != 0 && Cout == 32) return fail(fn, "Cout = 32 is supported in plain and heads mode only");
     if (mode == 0 && !out_f32 && !out_bf16) return fail(fn, "plain mode needs an output");
     if (mode == 1 && (!h_state || !out_f32 || !out_bf16)) return fail(fn, "gate mode needs h, u (fp32) and h*r (bf16) buffers");
     if (mode == 2 && (!h_state || !u_in || !out_f32)) return fail(fn, "out mode needs h, u and the new-state buffer");
@@ -350,6 +412,7 @@ extern "C" int forge_conv3d_tc(const void* x, long long x_batch_stride, int Cx, 
     p.B = B, p.D = D, p.H = H, p.W = W, p.Cout = Cout;
     p.nchunk_x = Cx / BK, p.nchunk = (Cx + Ch) / BK;
     p.mode = mode, p.lrelu = lrelu;
+    p.out_pitch = out_pitch, p.out_off = out_off;
     p.scale = scale, p.shift = shift, p.norm_shift = norm_shift, p.h = h_state, p.u_in = u_in;
     p.out_f32 = out_f32, p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16), p.out_norm = out_norm, p.aux = aux;
     {   // weights [27 * nchunk][Cout][64] bf16
@@ -370,9 +433,30 @@ extern "C" int forge_conv3d_tc(const void* x, long long x_batch_stride, int Cx, 
     if (Cout == 256) {
         if (int e = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(conv3d_tc_kernel<256>), Cfg<256>::SMEM)) return e;
         conv3d_tc_kernel<256><<<ctas, kThreads, Cfg<256>::SMEM, st>>>(maps, p);
+    } else if (Cout == 32) {
+        if (int e = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(conv3d_tc_kernel<32>), Cfg<32>::SMEM)) return e;
+        conv3d_tc_kernel<32><<<ctas, kThreads, Cfg<32>::SMEM, st>>>(maps, p);
     } else {
         if (int e = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(conv3d_tc_kernel<128>), Cfg<128>::SMEM)) return e;
         conv3d_tc_kernel<128><<<ctas, kThreads, Cfg<128>::SMEM, st>>>(maps, p);
     }
+    return check_launch(fn);
+}
+
+extern "C" int forge_conv3d_c8_to_1_relu(const float* x, const float* w, float bias, float* y, int B, int D, int H, int W,
+                                         void* stream) {
+    FORGE_RANGE("forge_conv3d_c8_to_1_relu");
+    using namespace forge;
+    const char* fn = "forge_conv3d_c8_to_1_relu";
+    if (!x || !w || !y) return fail(fn, "null pointer");
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(fn, "non-positive size");
+    if (!aligned16(x)) return fail(fn, "x must be 16-byte aligned");
+    const int sms = current_sm_count(fn);
+    if (sms <= 0) return 1;
+    const long long total = static_cast<long long>(B) * D * H * W;
+    const long long want = (total + 255) / 256;
+    const int grid = static_cast<int>(want < sms * 16ll ? want : sms * 16ll);
+    c3d::conv_c8_to_1_relu_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(x), w, bias, y, B,
+                                                                                      D, H, W);
     return check_launch(fn);
 }

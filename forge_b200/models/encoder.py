@@ -91,6 +91,25 @@ class Encoder3D(nn.Module):
         self._trunk_channels_last = True
         return self
 
+    def heads_tc_eligible(self, x):
+        """both heads on the tensor cores (ops.heads_tc): bf16 mode, eval-mode BN, no autograd graph wanted, tileable grid"""
+        _, c, d, h, w = x.shape
+        mods = (self.features_head, self.density_head)
+        wants_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for m in mods for p in m.parameters()))
+        return (self.compute_dtype == torch.bfloat16 and self.tc_fusion and x.is_cuda and c == 128 and not wants_graph
+                and not any(m.training for m in mods) and d % 4 == 0 and h % 4 == 0 and w % 8 == 0)
+
+    def get_render_volumes(self, x):
+        """(get_render_features(x), get_density3D(x)); one fused tensor-core path when eligible"""
+        if self.heads_tc_eligible(x):
+            from .. import ops
+            tensors = [t for m in (self.features_head, self.density_head) for t in list(m.parameters()) + list(m.buffers())]
+            key = tuple((t.data_ptr(), t._version) for t in tensors)
+            if getattr(self, '_heads_pack', None) is None or self._heads_pack[0] != key:
+                self._heads_pack = (key, ops.pack_heads_tc(self.features_head, self.density_head))
+            return ops.heads_tc(self._heads_pack[1], x)
+        return self.get_render_features(x), self.get_density3D(x)
+
     def get_density3D(self, z_3d):
         with self._amp():
             return self.density_head(z_3d).float()

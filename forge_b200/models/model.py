@@ -126,8 +126,7 @@ class FORGE(nn.Module):
         idxs = _view0_first(idxs)
         features_transformed = self.rotate.forward_views(voxels=features_raw, camPoses_cv2=camPoses_cv2, grid_size=D, order=idxs)
         features_mv = self.encoder_3d.fuse(features_transformed)
-        densities_mv = self.encoder_3d.get_density3D(features_mv)
-        features_mv = self.encoder_3d.get_render_features(features_mv)
+        features_mv, densities_mv = self.encoder_3d.get_render_volumes(features_mv)
         if self.config.dataset.name == 'omniobject3d':
             densities_mv = densities_mv.clamp(min=0.0, max=1.0)
         return features_mv, densities_mv

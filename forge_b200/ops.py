@@ -697,7 +697,7 @@ def conv3d_tc(x, wpack, mode, shift, h2=None, scale=None, lrelu=False, norm_shif
     ax = cl(torch.float32) if want_aux else None
     with torch.cuda.device(dev):
         _lib.call("forge_conv3d_tc", _ptr(xb), xbs, Cx, _ptr(hb), hbs, Ch, _ptr(wpack), m, int(bool(lrelu)), _ptr(scale),
-                  _ptr(shift), _ptr(norm_shift), _ptr(hs), _ptr(ui), _ptr(o32), _ptr(o16), _ptr(on), _ptr(ax), B, D, H, W, Cout,
+                  _ptr(shift), _ptr(norm_shift), _ptr(hs), _ptr(ui), _ptr(o32), _ptr(o16), _ptr(on), _ptr(ax), 0, 0, B, D, H, W, Cout,
                   int(max_ctas), _stream(x))
     view = lambda t: None if t is None else t.permute(0, 4, 1, 2, 3)     # noqa: E731
     if want_aux:
@@ -767,3 +767,68 @@ class _GruTC(torch.autograd.Function):
 def gru_tc(pk, h0, views):
     """fusion_norm(GRU(views; h0)) on the tensor cores with autograd support for views / h0 (weights are constants)."""
     return _GruTC.apply(pk, h0, *views)
+
+
+# ---- render heads on the tensor cores (inference): reference models/encoder.py:16-34 -----------------------------------------------
+def _convT_as_conv_weights(ct):
+    """ConvTranspose3d(Cin, 32, k 4, stride 2, pad 1) weight [Cin, 32, 4, 4, 4] -> the equivalent 3x3x3 convolution weight
+    [8 * 32, Cin, 3, 3, 3] whose 8 output groups are the 8 output parity classes (qz, qy, qx): out[2j + q] takes, per axis,
+    input j with tap 1 + q and input j - 1 (q = 0, tap 3) or j + 1 (q = 1, tap 0)."""
+    W = ct.weight.detach().float()
+    Cin, Co = W.shape[:2]
+    taps = {0: ((0, 1), (-1, 3)), 1: ((0, 2), (1, 0))}          # parity -> ((input offset, kernel tap), ...)
+    Weq = W.new_zeros(8 * Co, Cin, 3, 3, 3)
+    for q in range(8):
+        for dz, kz in taps[q >> 2]:
+            for dy, ky in taps[(q >> 1) & 1]:
+                for dx, kx in taps[q & 1]:
+                    Weq[q * Co:(q + 1) * Co, :, dz + 1, dy + 1, dx + 1] = W[:, :, kz, ky, kx].t()
+    return Weq
+
+
+def pack_heads_tc(features_head, density_head):
+    """weight / affine packs for heads_tc from the reference-shaped Sequentials (eval-mode BatchNorm folded)"""
+    ctf, bnf1, _, cf2, bnf2 = features_head
+    ctd, bnd1, _, cd2, bnd2, _, cd3, _ = density_head
+    with torch.no_grad():
+        def fold(conv, bn):
+            s = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
+            return s, ((conv.bias - bn.running_mean) * s + bn.bias).float()
+        sf1, bf1 = fold(ctf, bnf1)
+        sd1, bd1 = fold(ctd, bnd1)
+        sf2, bf2 = fold(cf2, bnf2)
+        sd2, bd2 = fold(cd2, bnd2)
+        dev = ctf.weight.device
+        W2 = torch.zeros(32, 64, 3, 3, 3, device=dev)
+        W2[0:16, 0:32] = cf2.weight.float()                   # render features read stem channels 0..31
+        W2[16:24, 32:64] = cd2.weight.float()                 # the density branch reads stem channels 32..63
+        return dict(
+            wf=pack_conv3d_weights(_convT_as_conv_weights(ctf)), sf=sf1.repeat(8).contiguous(), bf=bf1.repeat(8).contiguous(),
+            wd=pack_conv3d_weights(_convT_as_conv_weights(ctd)), sd=sd1.repeat(8).contiguous(), bd=bd1.repeat(8).contiguous(),
+            w2=pack_conv3d_weights(W2), s2=torch.cat([sf2, sd2, torch.ones(8, device=dev)]).contiguous(),
+            b2=torch.cat([bf2, bd2, torch.zeros(8, device=dev)]).contiguous(),
+            w3=cd3.weight.detach().float()[0].permute(1, 2, 3, 0).reshape(27, 8).contiguous(), b3=float(cd3.bias.item()))
+
+
+def heads_tc(pk, fused):
+    """fused [B,128,D,H,W] -> (render features [B,16,2D,2H,2W] fp32 channels-last, density [B,1,2D,2H,2W] fp32): both
+    transposed-convolution stems as 27-tap tcgen05 GEMMs with a pixel-shuffle epilogue into ONE 64-channel bf16 tensor, both second
+    convolutions as one 64 -> 32 GEMM, the 8 -> 1 density convolution + ReLU as a small direct kernel (4 launches; reference: 8
+    cuDNN convolutions / norms / activations)."""
+    _require_cuda(fused)
+    B, C, D, H, W = fused.shape
+    x, xbs = _bf16_cl(fused)
+    dev = fused.device
+    stem = torch.empty(B, 2 * D, 2 * H, 2 * W, 64, dtype=torch.bfloat16, device=dev)
+    feat = torch.empty(B, 2 * D, 2 * H, 2 * W, 16, dtype=torch.float32, device=dev)
+    d8 = torch.empty(B, 2 * D, 2 * H, 2 * W, 8, dtype=torch.float32, device=dev)
+    dens = torch.empty(B, 1, 2 * D, 2 * H, 2 * W, dtype=torch.float32, device=dev)
+    st = _stream(fused)
+    with torch.cuda.device(dev):
+        for w, s_, b_, off in ((pk['wf'], pk['sf'], pk['bf'], 0), (pk['wd'], pk['sd'], pk['bd'], 32)):
+            _lib.call("forge_conv3d_tc", _ptr(x), xbs, C, None, 0, 0, _ptr(w), 3, 1, _ptr(s_), _ptr(b_), None, None, None, None,
+                      _ptr(stem), None, None, 64, off, B, D, H, W, 256, 0, st)
+        _lib.call("forge_conv3d_tc", _ptr(stem), stem[0].numel(), 64, None, 0, 0, _ptr(pk['w2']), 4, 0, _ptr(pk['s2']), _ptr(pk['b2']),
+                  None, None, None, _ptr(feat), None, None, _ptr(d8), 0, 0, B, 2 * D, 2 * H, 2 * W, 32, 0, st)
+        _lib.call("forge_conv3d_c8_to_1_relu", _ptr(d8), _ptr(pk['w3']), pk['b3'], _ptr(dens), B, 2 * D, 2 * H, 2 * W, st)
+    return feat.permute(0, 4, 1, 2, 3), dens

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 16
+#define FORGE_ABI_VERSION 17
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -247,11 +247,22 @@ int forge_sample_points(const float* pts, int M, int D, int H, int W, int align_
  *   mode 2 (out):   Cout = C; c = tanh(acc + shift); h' = h_state (1 - u_in) + c u_in; out_f32 = h', out_bf16 = h' (nullable),
  *                   out_norm = h' * scale + norm_shift (nullable; fusion_norm in eval mode)
  *   aux (nullable, fp32 [..][C]): gate mode stores r, out mode stores c -- what the backward pass of the cell needs
+ *   mode 3 (shuffle): ConvTranspose3d(k 4, stride 2, pad 1) as a 27-tap GEMM with Cout = 8 parity classes x 32 channels
+ *                   (models/encoder.py:17, :26): columns [32 q, 32 q + 32) of input voxel (z, y, x) go, after scale / shift /
+ *                   LeakyReLU, to out_bf16[n][2z + qz][2y + qy][2x + qx][out_off .. out_off + 32) in rows of out_pitch channels
+ *   mode 4 (heads): Cout = 32: columns [0, 16) * scale + shift -> out_f32 [..][16]; columns [16, 24): + LeakyReLU -> aux [..][8]
+ *                   (the second convolutions of features_head / density_head over a 64-channel stem tensor, encoder.py:20-21, :29-31)
+ *   Cout = 32 is allowed in modes 0 and 4 only
  *   max_ctas: 0 = one persistent CTA per SM */
 int forge_conv3d_tc(const void* x, long long x_batch_stride, int Cx, const void* h2, long long h_batch_stride, int Ch,
                     const void* wpack, int mode, int lrelu, const float* scale, const float* shift,
                     const float* norm_shift, const float* h_state, const float* u_in, float* out_f32, void* out_bf16,
-                    float* out_norm, float* aux, int B, int D, int H, int W, int Cout, int max_ctas, void* stream);
+                    float* out_norm, float* aux, int out_pitch, int out_off, int B, int D, int H, int W, int Cout, int max_ctas,
+                    void* stream);
+
+/* Conv3d(8 -> 1, 3x3x3, pad 1) + ReLU on channels-last rows of 8 floats (last layer of density_head, models/encoder.py:32-33);
+ * w [27][8] = weight[0][ci][dz][dy][dx] at [(dz*3+dy)*3+dx][ci]; y [B][D][H][W] */
+int forge_conv3d_c8_to_1_relu(const float* x, const float* w, float bias, float* y, int B, int D, int H, int W, void* stream);
 
 /* Elementwise stages of the backward pass of the tensor-core ConvGRU cell (constant weights), dense channels-last rows
  * [N = B D H W][C] fp32 unless noted; between them run the two transposed convolutions (forge_conv3d_tc, plain mode):

@@ -153,3 +153,29 @@ def test_lift_convolution_on_tensor_cores_matches_reference_within_bf16_toleranc
         ref = m.conv1(z)                        # fp32 cuDNN on the same trunk output
     assert got.shape == ref.shape
     assert _err(got, ref) <= 2e-2
+
+
+def test_heads_on_tensor_cores_match_reference_within_bf16_tolerance():
+    """features_head / density_head (ConvTranspose3d k4 s2 as a 27-tap GEMM with pixel-shuffle epilogue, merged second
+    convolutions, 8 -> 1 density convolution) against the fp32 reference fixture and against the fp32 module on a larger grid"""
+    g = load_golden("encoder_small")
+    s = g['seed']
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = seeded.load_seeded(Encoder3D(syn.make_config()), s).to(DEV).eval()
+    m.compute_dtype = torch.bfloat16
+    fused = g['fused'].to(DEV)
+    with torch.no_grad():
+        assert m.heads_tc_eligible(fused)
+        rfeat, dens = m.get_render_volumes(fused)
+    assert rfeat.shape == g['rfeat'].shape and dens.shape == g['dens'].shape
+    assert _err(rfeat, g['rfeat']) <= 2e-2
+    assert _err(dens, g['dens']) <= 2e-2
+    assert (dens >= 0).all()
+    x = torch.randn(2, 128, 16, 12, 24, device=DEV)
+    with torch.no_grad():
+        rf, dn = m.get_render_volumes(x)
+        m.compute_dtype = None
+        rf0, dn0 = m.get_render_features(x), m.get_density3D(x)
+    assert rf.shape == rf0.shape and dn.shape == dn0.shape
+    assert _err(rf, rf0) <= 2e-2 and _err(dn, dn0) <= 2e-2

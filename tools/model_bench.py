@@ -81,8 +81,7 @@ def main():
             ev[2].record()
             fmv = model.encoder_3d.fuse(rot)
             ev[3].record()
-            dens = model.encoder_3d.get_density3D(fmv)
-            feat = model.encoder_3d.get_render_features(fmv)
+            feat, dens = model.encoder_3d.get_render_volumes(fmv)
             ev[4].record()
             E = sample['cam_extrinsics_cv2_canonicalized'].reshape(b * t_all, 4, 4)
             cam = {'R': E[:, :3, :3], 'T': E[:, :3, 3], 'K': sample['K_cv2'].reshape(b * t_all, 3, 3).clone()}
@@ -90,7 +89,7 @@ def main():
             model.render(cam, feat, dens, return_origin_proj=True, view2vol=v2v)
             ev[5].record()
             torch.cuda.synchronize()
-        names = ["lift (ResNet50 + 3-D conv, cuDNN)", "sort + rotate (K2)", "fuse (ConvGRU)", "heads (cuDNN)",
+        names = ["lift (ResNet50 + 3-D conv, cuDNN)", "sort + rotate (K2)", "fuse (ConvGRU)", "heads",
                  "render (camera prep + pack + K1 + decoder + upsample)"]
         return {n: round(ev[i].elapsed_time(ev[i + 1]), 3) for i, n in enumerate(names)}
     stage_breakdown()
