@@ -175,3 +175,25 @@ def test_graphed_refine_iteration_matches_eager_loop():
     # 20 Adam steps of 1e-3 move a parameter by up to 2e-2; Adam's normalisation amplifies gradient noise on near-zero components
     assert (r.quat - q).abs().max().item() <= 1e-3 and (r.trans - t).abs().max().item() <= 1e-3
     assert (r.quat - q0).abs().max().item() > 1e-3              # and the parameters did move
+
+
+def test_forge_forward_bf16_tensor_core_configuration_tracks_fp32(setup):
+    """the whole inference configuration that runs on the tensor cores (lift convolution, ConvGRU fusion, heads, decoder in bf16
+    with fp32 accumulation) against the fp32 forward of the same model: images agree to bf16 accuracy and are not empty"""
+    import copy
+    cfg, model, sample = setup
+    model = copy.deepcopy(model).eval()
+    model.encoder_3d.density_head[6].bias.data.fill_(0.1)        # random-init heads end in ReLU: keep the density volume non-empty
+    m16 = copy.deepcopy(model)
+    m16.encoder_3d.channels_last_3d_()
+    m16.encoder_3d.compute_dtype = torch.bfloat16
+    m16.render.decoder_dtype = torch.bfloat16
+    with torch.no_grad():
+        rgb, mask = model(sample, None, DEV)
+        rgb16, mask16 = m16(sample, None, DEV)
+        feats = m16.lift(sample['images'][:, :5].to(DEV))
+        assert m16.encoder_3d.heads_tc_eligible(torch.zeros(1, 128, 32, 32, 32, device=DEV))
+    assert mask.max().item() > 0.05 and mask16.max().item() > 0.05
+    assert (mask16 - mask).abs().max().item() <= 5e-2 * max(1.0, mask.abs().max().item())
+    assert (rgb16 - rgb).abs().max().item() <= 5e-2 * max(1.0, rgb.abs().max().item())
+    assert (mask16 - mask).abs().mean().item() <= 5e-3

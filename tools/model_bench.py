@@ -60,7 +60,12 @@ def main():
     sample = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in sample.items()}
     out = {"bench": "FORGE.forward, %d objects x 5 input views -> %d rendered views, 256^2 images, GT poses" % (b, t_all)}
 
+    K0 = sample['K_cv2'].clone()
+
     def fwd():
+        # VolRender.forward halves the caller's K in place (reference models/volume_render.py:50-51) and .to(device) of a tensor
+        # that already lives on the device is the same tensor: hand every call a fresh copy
+        sample['K_cv2'] = K0.clone()
         with torch.no_grad():
             return model(sample, None, DEV)
 
@@ -84,7 +89,7 @@ def main():
             feat, dens = model.encoder_3d.get_render_volumes(fmv)
             ev[4].record()
             E = sample['cam_extrinsics_cv2_canonicalized'].reshape(b * t_all, 4, 4)
-            cam = {'R': E[:, :3, :3], 'T': E[:, :3, 3], 'K': sample['K_cv2'].reshape(b * t_all, 3, 3).clone()}
+            cam = {'R': E[:, :3, :3], 'T': E[:, :3, 3], 'K': K0.reshape(b * t_all, 3, 3).clone()}
             v2v = torch.arange(b, device=DEV).repeat_interleave(t_all).int()
             model.render(cam, feat, dens, return_origin_proj=True, view2vol=v2v)
             ev[5].record()
@@ -112,7 +117,7 @@ def main():
                 fa = feat.unsqueeze(1).repeat(1, t_all, 1, 1, 1, 1).reshape(b * t_all, *feat.shape[1:])
                 da = dens.unsqueeze(1).repeat(1, t_all, 1, 1, 1, 1).reshape(b * t_all, *dens.shape[1:])
                 E = sample['cam_extrinsics_cv2_canonicalized'].reshape(b * t_all, 4, 4)
-                cam = {'R': E[:, :3, :3], 'T': E[:, :3, 3], 'K': sample['K_cv2'].reshape(b * t_all, 3, 3).clone()}
+                cam = {'R': E[:, :3, :3], 'T': E[:, :3, 3], 'K': K0.reshape(b * t_all, 3, 3).clone()}
                 return rp.volrender_forward(ren, model.render.conv_rgb, cam, fa, da, 256, 1.0, return_origin_proj=True)
         out["reference op sequence (oracle on GPU, same cuDNN lift/fuse/heads) ms"] = round(timed(ref, max(2, args.iters // 2)), 3)
 
@@ -123,6 +128,7 @@ def main():
 
         def step():
             model.zero_grad(set_to_none=True)
+            sample['K_cv2'] = K0.clone()
             rgb, mask = model(sample, None, DEV)
             (F.mse_loss(rgb, tgt_rgb) + F.mse_loss(mask, tgt_mask)).backward()
         out["forge_b200 fp32 train fwd+bwd ms"] = round(timed(step, max(2, args.iters // 2)), 3)
