@@ -47,12 +47,14 @@ def _compare(inp, img, D, P, **kw):
 
 
 @pytest.mark.parametrize("objects,views,img,D,P,dense", [
+    (1, 2, 16, 4, 8, False),          # tiny: the volume is smaller than every TMA box shape, 8 x 8 rays
     (1, 3, 64, 16, 24, False),        # small
     (2, 2, 32, 10, 16, True),         # sigma > 1: sign-alternating transmittance
     (1, 5, 128, 32, 32, False),       # cfg-1
     (1, 2, 70, 20, 33, False),        # 35 x 35 rays: partial tiles in both directions, odd sample count
     (4, 5, 256, 64, 64, False),       # cfg-2
     (2, 5, 256, 64, 64, True),        # cfg-2 geometry, dense volume
+    (2, 3, 512, 128, 128, False),     # cfg-4 geometry (BASELINE.json configs[3] sizes per view / volume)
 ])
 def test_tma_matches_gather(objects, views, img, D, P, dense):
     inp = syn.render_inputs(objects, views, img, D, seed=3, dense=dense, device=DEV)
