@@ -6,7 +6,7 @@
 //     a slab form a frustum segment whose voxel footprint is bounded by the axis-aligned box of its 8 vertices (positions
 //     are multilinear in pixel and depth).  The brick is fetched from the packed volume as z-planes of a static in-plane
 //     shape, one cp.async.bulk.tensor (UTMALDG) per plane, into a 2-stage shared-memory ring; slab lengths adapt so that
-//     every brick fits its stage (<= 832 voxels = 52 KB).
+//     every brick fits its stage (<= 880 voxels = 55 KB).
 //   * a ninth warp is the producer: it waits for a stage to be released (empty mbarrier, one arrival per consumer warp),
 //     issues the copies of the next slab (planned while the previous copies were in flight) and plans the one after it.
 //     (Variant without a producer warp -- the last consumer warp to finish a slab refills the stage, 128 registers per
@@ -40,7 +40,7 @@ struct TmaMaps {
 };
 
 // kStages x kStageVox voxels (64 B each) of brick ring per CTA; two CTAs per SM
-template <int kStages, int kStageVox, int kWarpsY>
+template <int kStages, int kStageVox, int kWarpsY, bool kPrefetch = true>
 __global__ void __launch_bounds__(32 * (4 * kWarpsY + 1), kWarpsY <= 2 ? 2 : 1)
 raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __restrict__ feat_pad,
                         const float4* __restrict__ dens_quad,
@@ -196,7 +196,7 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
     Foot fn;
     float4 d4n = make_float4(0.f, 0.f, 0.f, 0.f);
     bool actn = false;
-    if (kw1 > kw0) actn = fetch(max(kt0, kw0), fn, d4n);
+    if (kPrefetch && kw1 > kw0) actn = fetch(max(kt0, kw0), fn, d4n);
 
     for (int s = 0;; ++s) {
         const int st = s % kStages;
@@ -206,10 +206,11 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
         const int kend = min(h.kb, kw1);
         for (int k = max(h.ka, kw0); k < kend; ++k) {
             const float z = sm.zs[k];
+            if (!kPrefetch) actn = fetch(k, fn, d4n);
             const Foot f = fn;
             const bool act = actn;
             const float4 d4 = d4n;
-            if (k + 1 < kw1) actn = fetch(k + 1, fn, d4n);
+            if (kPrefetch && k + 1 < kw1) actn = fetch(k + 1, fn, d4n);
             const float w00 = __fmul_rn(f.wx0, f.wy0), w10 = __fmul_rn(f.wx1, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1),
                         w11 = __fmul_rn(f.wx1, f.wy1);
             float part = 0.f;
@@ -275,18 +276,18 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
     }
 }
 
-template <int kStages, int kStageVox, int kWarpsY>
+template <int kStages, int kStageVox, int kWarpsY, bool kPrefetch = true>
 static int tma_launch_cfg(const char* fn, const TmaMaps& maps, const float* feat_pad, const float4* dens_quad,
                           const int* view2vol, const float* cam12, const float* zs, float* out_feat, float* out_sil,
                           float* out_depth, int N, int V, int D, int H, int W, int S_h, int S_w, int P, cudaStream_t st) {
     constexpr int bytes = tma_smem_bytes(kStages, kStageVox), kTH = 4 * kWarpsY, threads = 32 * (4 * kWarpsY + 1);
     static_assert((kWarpsY <= 2 ? 2 : 1) * bytes <= 227 * 1024 && kStages <= kMaxStages, "the CTAs of an SM must fit");
     static_assert(kStageVox >= 16 * 16, "a stage must hold one plane of the largest shape");
-    if (int e = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(raymarch_fwd_tma_kernel<kStages, kStageVox, kWarpsY>), bytes))
+    if (int e = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(raymarch_fwd_tma_kernel<kStages, kStageVox, kWarpsY, kPrefetch>), bytes))
         return e;
     const int tiles_x = (S_w + kTW - 1) / kTW, tiles_y = (S_h + kTH - 1) / kTH;
     dim3 grid(tiles_x * tiles_y, N);
-    raymarch_fwd_tma_kernel<kStages, kStageVox, kWarpsY><<<grid, threads, bytes, st>>>(
+    raymarch_fwd_tma_kernel<kStages, kStageVox, kWarpsY, kPrefetch><<<grid, threads, bytes, st>>>(
         maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, D, H, W, S_h, S_w, P, tiles_x,
         interleave_views(V, D, H, W));
     return check_launch(fn);
@@ -322,10 +323,17 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
 #define FORGE_K1T(S, VOX, WY)                                                                                                \
     return tma_launch_cfg<S, VOX, WY>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D, H, \
                                       W, S_h, S_w, P, st)
+    if (ring == 8)          // 880-voxel stages (the most two CTAs per SM can hold)
+        return tma_launch_cfg<2, 880, 2>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D, H, W,
+                                         S_h, S_w, P, st);
+    if (ring == 9)          // no software pipelining of the density quad
+        return tma_launch_cfg<2, 832, 2, false>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D,
+                                                H, W, S_h, S_w, P, st);
     if (ring == 3) FORGE_K1T(3, 552, 2);
     if (ring == 5) FORGE_K1T(2, 1700, 4);         // 16 x 16 pixel tile, one CTA per SM, twice the slab length
     if (ring == 6) FORGE_K1T(3, 1130, 4);
-    FORGE_K1T(2, 832, 2);
+    if (ring == 1) FORGE_K1T(2, 832, 2);
+    FORGE_K1T(2, 880, 2);         // default: the largest stages two CTAs per SM can hold (0.347 vs 0.349 ms at cfg-2, 4.68 vs 4.73 ms at cfg-4)
 #undef FORGE_K1T
 }
 
