@@ -186,6 +186,38 @@ def golden_pose3d_model(name, seed, train_heads):
     print(name, tuple(rgb.shape), "rgb max", float(rgb.max()), "mask max", float(mask.max()))
 
 
+def golden_joint_model(name, seed):
+    """Reference FORGE.forward (models/model.py:42-148) with PREDICTED poses: both pose networks + pose head -> canonical pose
+    algebra -> rotate -> distance-sorted fuse -> heads -> 5 input + 2 novel views."""
+    from models.model import FORGE                        # the reference module, unmodified
+    from oracle import seeded
+    from forge_b200 import synthetic as syn
+    cfg = _cfg(256, 32)
+    cfg.train = SimpleNamespace(use_gt_pose=False, canonicalize=True, parameter='joint')
+    cfg.network.rot_representation = 'quat'
+    torch.manual_seed(seed)
+    ref = seeded.load_seeded(FORGE(cfg), seed).eval()
+    ref.encoder_3d.density_head[6].bias.data.fill_(0.1)
+    sample = syn.kubric_batch(1, n_views_all=7, img_size=256, seed=seed)
+
+    class _DS:      # the two dataset helpers forward() calls (reference dataset/kubric.py:448-452)
+        ext = torch.eye(4)
+        ext[2, 3] = cfg.render.camera_z
+
+        def get_canonical_extrinsics_cv2(self, device='cpu'):
+            return self.ext.to(device)
+
+        def get_canonical_pose_cv2(self, device='cpu'):
+            return torch.inverse(self.ext).to(device)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rgb, mask, oproj, poses = ref(sample, _DS(), 'cpu')
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(dict(
+        seed=seed, rgb_sub=seeded.subsample(rgb), mask_sub=seeded.subsample(mask), rgb_mean=rgb.mean(dim=(1, 2, 3)),
+        mask_mean=mask.mean(dim=(1, 2, 3)), origin_proj=oproj, pose_pred=poses['pred'], pose_gt=poses['gt'], pose_conf=poses['conf'])))
+    print(name, tuple(rgb.shape), "mask max", float(mask.max()), "pred", poses['pred'][0].tolist())
+
+
 def golden_mat2quat(name, seed):
     """utils/geo_utils.mat2quat (:140-207) including rotations by exactly / nearly 180 degrees."""
     from utils import geo_utils                           # the reference module, unmodified
@@ -210,6 +242,10 @@ def main(which=None):
     sys.path.insert(0, REF)
     os.makedirs(OUT, exist_ok=True)
     _offline_torchvision()
+    # the reference's pose_estimator_2d.py:96 fetches ResNet weights through model_zoo: reuse compat's offline fallback
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("forge_compat_site", os.path.join(ROOT, "compat", "sitecustomize.py"))
+    spec.loader.exec_module(importlib.util.module_from_spec(spec))
     if not hasattr(np, 'float'):          # the reference's models/model_utils.py:45 still uses the removed alias
         np.float = float
     jobs = dict(
@@ -224,6 +260,7 @@ def main(which=None):
         pose3d_model_eval=lambda: golden_pose3d_model("pose3d_model_eval", seed=33, train_heads=False),
         pose3d_model_train=lambda: golden_pose3d_model("pose3d_model_train", seed=34, train_heads=True),
         mat2quat=lambda: golden_mat2quat("mat2quat", seed=35),
+        joint_model_eval=lambda: golden_joint_model("joint_model_eval", seed=36),
     )
     for k in (which or jobs):
         jobs[k]()

@@ -26,3 +26,57 @@ def test_reference_demo_py_runs_unchanged():
     summary = json.loads(last[-1])
     assert summary["rc"] == 0
     assert summary["gifs"] == ["0_0.gif", "1_0.gif", "2_0.gif"]          # one 360-degree render per demo case
+
+
+JOINT = r'''
+import sys, warnings, numpy as np, torch
+warnings.simplefilter("ignore")
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+from types import SimpleNamespace as NS
+from oracle import seeded
+from forge_b200 import synthetic as syn
+from models.model import FORGE                      # compat: forge_b200 FORGE + the reference's own pose networks
+seed = int(sys.argv[1])
+cfg = syn.make_config(img_size=256, n_pts_per_ray=32, use_gt_pose=False, parameter='joint')
+cfg.network.rot_representation = 'quat'
+m = seeded.load_seeded(FORGE(cfg), seed).cuda().eval()
+m.encoder_3d.density_head[6].bias.data.fill_(0.1)
+sample = syn.kubric_batch(1, n_views_all=7, img_size=256, seed=seed)
+class DS:
+    ext = torch.eye(4); ext[2, 3] = cfg.render.camera_z
+    def get_canonical_extrinsics_cv2(self, device='cpu'): return self.ext.to(device)
+    def get_canonical_pose_cv2(self, device='cpu'): return torch.inverse(self.ext).to(device)
+with torch.no_grad():
+    rgb, mask, oproj, poses = m(sample, DS(), 'cuda')
+np.savez(sys.argv[2], rgb_sub=seeded.subsample(rgb).cpu().numpy(), mask_sub=seeded.subsample(mask).cpu().numpy(),
+         origin_proj=oproj.cpu().numpy(), pose_pred=poses['pred'].cpu().numpy(), pose_gt=poses['gt'].cpu().numpy(),
+         pose_conf=poses['conf'].cpu().numpy())
+'''
+
+
+@pytest.mark.skipif(not HAVE, reason="no reference checkout / staged tarball (the pose networks are the reference's own)")
+def test_joint_model_with_predicted_poses_matches_reference_values(tmp_path):
+    """FORGE.forward with PREDICTED poses (both pose networks + pose head -> canonical pose algebra -> rotate -> sorted fuse ->
+    heads -> 5 input + 2 novel views) against the output of the unmodified reference FORGE on CPU (tests/golden/
+    joint_model_eval.npz, oracle/make_golden.py); seeded weights on both sides."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import run_reference_script as rrs
+    ref = rrs.stage(str(tmp_path))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "joint_model_eval.npz"))
+    out = str(tmp_path / "joint.npz")
+    res = subprocess.run([sys.executable, "-c", JOINT, str(int(g['seed'])), out], cwd=ref, env=rrs.env_for(ref),
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-3000:]
+    o = np.load(out)
+    # the pose networks are the reference's code on both sides: predictions agree to fp32 (GPU vs CPU) accuracy
+    assert np.abs(o['pose_pred'] - g['pose_pred']).max() <= 2e-3
+    assert np.abs(o['pose_gt'] - g['pose_gt']).max() <= 1e-5
+    assert np.abs(o['origin_proj'] - g['origin_proj']).max() <= 5e-3
+    for k in ('rgb_sub', 'mask_sub'):
+        ref_v = g[k]
+        assert o[k].shape == ref_v.shape
+        assert np.abs(o[k] - ref_v).max() <= 2e-2 * max(1.0, np.abs(ref_v).max()), k       # images through predicted poses
+        assert np.abs(o[k] - ref_v).mean() <= 1e-3, k
+    assert g['mask_sub'].max() > 0.5
