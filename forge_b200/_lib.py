@@ -25,7 +25,7 @@ _SIGNATURES = {
     "forge_raymarch_fwd_gather": (_c.c_int, [_F] * 8 + [_I] * 8 + [_F]),
     "forge_raymarch_fwd_tma": (_c.c_int, [_F] * 8 + [_I] * 8 + [_F]),
     "forge_raymarch_bwd": (_c.c_int, [_F] * 12 + [_I] * 8 + [_F]),
-    "forge_raymarch_bwd_workspace": (_c.c_longlong, [_I] * 4),
+    "forge_raymarch_bwd_workspace": (_c.c_longlong, [_I] * 8),
     "forge_rotate_fwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F] + [_I] * 5 + [_F]),
     "forge_rotate_bwd": (_c.c_int, [_F] * 6 + [_c.c_float, _F, _F, _F] + [_I] * 5 + [_F]),
     "forge_decoder_wpack_floats": (_c.c_int, []),
@@ -49,7 +49,7 @@ _SIGNATURES = {
     "forge_gru_tc_bwd": (_c.c_int, [_I] + [_F] * 8 + [_c.c_longlong, _I, _F]),
     "forge_sample_points": (_c.c_int, [_F, _I, _I, _I, _I, _I, _F, _F, _F]),
 }
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 _lock = threading.Lock()
 _lib = None

@@ -17,6 +17,7 @@
 // The two lanes split the density planes (dz = c) and combine with one xor-shuffle.  Samples outside
 // the exact ray/volume slab are skipped: under zeros padding they contribute exactly 0 and multiply
 // the transmittance by exactly 1.
+#include <algorithm>
 #include <cstdlib>
 
 #include "raymarch_common.cuh"
@@ -144,16 +145,22 @@ raymarch_fwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
 constexpr int kBwThreads = 128;                 // 4 warps = 16x4 pixel tile (finer CTAs balance better than 16x8)
 constexpr int kRaysPerCta = kBwThreads / 2;
 
+// kMerge: rays of a warp whose samples share the base voxel (0.5-voxel ray spacing: 16 rays of a 4x4 patch fall into ~6.7 distinct
+// base voxels) are summed by one leader pair before the RED: REDs cost ~1.2 cycles per active lane in the LSU whatever their
+// width, and that issue rate -- not L2 -- bounded the unmerged kernel (20 RED warp-instructions x 32 lanes per 16 ray-samples).
+template <bool kMerge>
 __global__ void __launch_bounds__(kBwThreads, 4)
 raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict__ dens_quad,
                     const int* __restrict__ view2vol, const float* __restrict__ cam12, const float* __restrict__ zs_g,
                     const float* __restrict__ g_feat, const float* __restrict__ g_sil,
                     const float* __restrict__ g_depth, float* __restrict__ grad_feat_pad,
                     float* __restrict__ grad_dens_pad, float* __restrict__ grad_cam, float* __restrict__ workspace,
-                    int D, int H, int W, int Sh, int Sw, int P, int tiles_x, int interleave) {
+                    float4* __restrict__ grad_quad, int D, int H, int W, int Sh, int Sw, int P, int tiles_x, int interleave) {
     __shared__ float zs[kMaxP];
     __shared__ float cam[12];
     __shared__ float red[12 * (kBwThreads / 32)];
+    __shared__ __align__(16) float gFs[kMerge ? kRaysPerCta * 16 : 4];   // upstream feature gradient per ray, in scatter order
+    __shared__ __align__(16) float cws[kMerge ? kRaysPerCta * 8 : 4];    // this sample's 8 corner weights (x w_k) per ray
     // per-CTA stash [P][3][64 rays] in the caller's workspace (L2-resident between the two passes);
     // keeping it out of shared memory leaves the whole unified L1 to the corner gathers
     float* stash = workspace + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * P * 3 * kRaysPerCta;
@@ -188,6 +195,7 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
     const float* fv = feat_pad + volp * 16 + c * 8;
     const float4* qv = dens_quad + v * (D + 2) * Hq * Wq;
     float* gdv = need_dens ? grad_dens_pad + volp : nullptr;
+    float4* gqv = (need_dens && grad_quad) ? grad_quad + v * (D + 2) * Hq * Wq : nullptr;    // dens_quad layout (kernel-side scratch)
     const int row_y = Wp * 16, row_z = Hp * Wp * 16;
 
     float gF[8];
@@ -218,6 +226,12 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
         sB[e] = c ? mine_hi : other_lo;     // channels 8+4c+e of the ray:    c=0 -> lane1's gF[e], c=1 -> own gF[4+e]
     }
     float* gfs = need_feat ? grad_feat_pad + volp * 16 + c * 4 : nullptr;
+    if (kMerge && need_feat) {
+        float4* g = reinterpret_cast<float4*>(&gFs[(ray * 2 + c) * 8]);
+        g[0] = make_float4(sA[0], sA[1], sA[2], sA[3]);
+        g[1] = make_float4(sB[0], sB[1], sB[2], sB[3]);
+        __syncwarp();                   // read back by lanes of the same warp only
+    }
 
     // ---- pass A: front to back ----
     float T = 1.f;
@@ -239,9 +253,11 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
         const float sigma = part + __shfl_xor_sync(0xffffffffu, part, 1);
         const float wk = sigma * T;
         float a_part = 0.f, gix = 0.f, giy = 0.f, giz = 0.f;
+        float cwv[4] = {0.f, 0.f, 0.f, 0.f};         // kMerge: w_k x weight of the corners of plane dz = c
+        int off = 0;
         if (act) {
             const bool scatter = need_feat && (wk != 0.f);
-            const int off = ((f.z0 + 1) * Hp + (f.y0 + 1)) * row_y + (f.x0 + 1) * 16;
+            off = ((f.z0 + 1) * Hp + (f.y0 + 1)) * row_y + (f.x0 + 1) * 16;
 #pragma unroll
             for (int cn = 0; cn < 8; ++cn) {
                 const int o = off + ((cn & 4) ? row_z : 0) + ((cn & 2) ? row_y : 0) + ((cn & 1) ? 16 : 0);
@@ -256,10 +272,48 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
                 gix = fmaf((cn & 1) ? wy * wz : -(wy * wz), qd, gix);
                 giy = fmaf((cn & 2) ? wx * wz : -(wx * wz), qd, giy);
                 giz = fmaf((cn & 4) ? wxy : -wxy, qd, giz);
-                if (scatter) {
+                if (kMerge) {
+                    if ((cn >> 2) == c) cwv[cn & 3] = wk * w;
+                } else if (scatter) {
                     const float cw = wk * w;
                     red_add_v4(gfs + o, make_float4(cw * sA[0], cw * sA[1], cw * sA[2], cw * sA[3]));
                     red_add_v4(gfs + o + 8, make_float4(cw * sB[0], cw * sB[1], cw * sB[2], cw * sB[3]));
+                }
+            }
+        }
+        if (kMerge && need_feat) {          // warp-uniform: every lane takes part in the match
+            const bool scat = act && (wk != 0.f);
+            __syncwarp();                   // the previous sample's reads of cws are done
+            if (scat) *reinterpret_cast<float4*>(&cws[ray * 8 + 4 * c]) = make_float4(cwv[0], cwv[1], cwv[2], cwv[3]);
+            const unsigned grp = __match_any_sync(0xffffffffu, scat ? off : ~lane);      // lanes (ray pairs) with the same base voxel
+            __syncwarp();
+            if (scat && (lane >> 1) == ((__ffs(grp) - 1) >> 1)) {       // leader pair of the group: lane c adds its 4 + 4 channels
+                const unsigned members = grp & 0x55555555u;              // one bit per member ray
+#pragma unroll
+                for (int hz = 0; hz < 2; ++hz) {
+                    float4 a[4], b[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) a[e] = b[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (unsigned rr = members; rr; rr &= rr - 1) {
+                        const int mray = (warp * 32 + __ffs(rr) - 1) >> 1;
+                        const float4 w4 = *reinterpret_cast<const float4*>(&cws[mray * 8 + 4 * hz]);
+                        const float4 ga = *reinterpret_cast<const float4*>(&gFs[(mray * 2 + c) * 8]);
+                        const float4 gb = *reinterpret_cast<const float4*>(&gFs[(mray * 2 + c) * 8 + 4]);
+                        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            a[e].x = fmaf(wv[e], ga.x, a[e].x), a[e].y = fmaf(wv[e], ga.y, a[e].y);
+                            a[e].z = fmaf(wv[e], ga.z, a[e].z), a[e].w = fmaf(wv[e], ga.w, a[e].w);
+                            b[e].x = fmaf(wv[e], gb.x, b[e].x), b[e].y = fmaf(wv[e], gb.y, b[e].y);
+                            b[e].z = fmaf(wv[e], gb.z, b[e].z), b[e].w = fmaf(wv[e], gb.w, b[e].w);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int o = off + (hz ? row_z : 0) + ((e & 2) ? row_y : 0) + ((e & 1) ? 16 : 0);
+                        red_add_v4(gfs + o, a[e]);
+                        red_add_v4(gfs + o + 8, b[e]);
+                    }
                 }
             }
         }
@@ -295,7 +349,11 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
             const float dsig = Tk * (a - Bk);
             Bk = fmaf(a, sigma, (1.f - sigma) * Bk);
             const float wz = c ? f.wz1 : f.wz0;
-            if (need_dens) {
+            if (need_dens && gqv) {         // one 16-byte RED per lane instead of four scalar ones (REDs cost per lane, not per byte)
+                const float dz = dsig * wz;
+                red_add_v4(reinterpret_cast<float*>(gqv + (static_cast<long long>(f.z0 + 1 + c) * Hq + (f.y0 + 1)) * Wq + (f.x0 + 1)),
+                           make_float4(dz * (f.wx0 * f.wy0), dz * (f.wx1 * f.wy0), dz * (f.wx0 * f.wy1), dz * (f.wx1 * f.wy1)));
+            } else if (need_dens) {
                 float* g = gdv + (static_cast<long long>(f.z0 + 1 + c) * Hp + (f.y0 + 1)) * Wp + (f.x0 + 1);
                 const float dz = dsig * wz;
                 atomicAdd(g, dz * (f.wx0 * f.wy0));
@@ -341,6 +399,32 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
             atomicAdd(grad_cam + n * 12 + threadIdx.x, x);
         }
     }
+}
+
+// grad_dens_pad[zp][Y][X] += the four quad components that alias padded voxel (zp, Y, X): quad (zp, yq, xq) holds the
+// gradients of the padded voxels (yq, xq), (yq, xq+1), (yq+1, xq), (yq+1, xq+1), yq in [0, H], xq in [0, W].
+__global__ void __launch_bounds__(256)
+fold_dens_quads_kernel(const float4* __restrict__ quad, float* __restrict__ grad_dens_pad, long long planes, int H, int W) {
+    const int Hp = H + 2, Wp = W + 2, Hq = H + 1, Wq = W + 1;
+    const long long total = planes * Hp * Wp;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+        const int X = static_cast<int>(i % Wp), Y = static_cast<int>((i / Wp) % Hp);
+        const float4* q = quad + (i / (static_cast<long long>(Wp) * Hp)) * Hq * Wq;
+        float g = 0.f;
+        if (Y < Hq && X < Wq) g += q[Y * Wq + X].x;
+        if (Y < Hq && X >= 1) g += q[Y * Wq + X - 1].y;
+        if (Y >= 1 && X < Wq) g += q[(Y - 1) * Wq + X].z;
+        if (Y >= 1 && X >= 1) g += q[(Y - 1) * Wq + X - 1].w;
+        grad_dens_pad[i] += g;
+    }
+}
+
+static long long bwd_stash_bytes(int N, int S_h, int S_w, int P) {
+    const long long tiles = static_cast<long long>((S_w + 15) / 16) * ((S_h + 3) / 4);
+    return tiles * N * P * 3 * kRaysPerCta * static_cast<long long>(sizeof(float));
+}
+static long long bwd_quad_bytes(int V, int D, int H, int W) {
+    return static_cast<long long>(V) * (D + 2) * (H + 1) * (W + 1) * 16;
 }
 
 static int raymarch_check(const char* fn, int N, int V, int D, int H, int W, int S_h, int S_w, int P) {
@@ -455,11 +539,10 @@ extern "C" int forge_raymarch_fwd(const float* feat_pad, const float* dens_quad,
                                                 H, W, S_h, S_w, P, stream);
 }
 
-extern "C" long long forge_raymarch_bwd_workspace(int N, int S_h, int S_w, int P) {
+extern "C" long long forge_raymarch_bwd_workspace(int N, int V, int D, int H, int W, int S_h, int S_w, int P) {
     using namespace forge;
-    if (N <= 0 || S_h <= 0 || S_w <= 0 || P <= 0) return 0;
-    const long long tiles = static_cast<long long>((S_w + 15) / 16) * ((S_h + 3) / 4);
-    return tiles * N * P * 3 * kRaysPerCta * static_cast<long long>(sizeof(float));
+    if (N <= 0 || V <= 0 || D <= 0 || H <= 0 || W <= 0 || S_h <= 0 || S_w <= 0 || P <= 0) return 0;
+    return bwd_stash_bytes(N, S_h, S_w, P) + bwd_quad_bytes(V, D, H, W);
 }
 
 extern "C" int forge_raymarch_bwd(const float* feat_pad, const float* dens_quad, const int* view2vol,
@@ -480,8 +563,31 @@ extern "C" int forge_raymarch_bwd(const float* feat_pad, const float* dens_quad,
         return fail(fn, "feat_pad must be 32-byte aligned, dens_quad / g_feat / grad_feat_pad 16-byte aligned");
     const int tiles_x = (S_w + 15) / 16, tiles_y = (S_h + 3) / 4;
     dim3 grid(tiles_x * tiles_y, N);
-    raymarch_bwd_kernel<<<grid, kBwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        feat_pad, reinterpret_cast<const float4*>(dens_quad), view2vol, cam12, zs, g_feat, g_sil, g_depth, grad_feat_pad,
-        grad_dens_pad, grad_cam12, workspace, D, H, W, S_h, S_w, P, tiles_x, interleave_views(V, D, H, W));
+    static const int merge = [] {          // tuning knob (development): bit 0 = same-base merge of the feature REDs,
+        const char* e = getenv("FORGE_K1B_MERGE");      // bit 1 = density gradient through quads; 0 = the round-1 scatter
+        return e ? atoi(e) : 3;
+    }();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // density gradient: accumulated as quads in the workspace (behind the stash), folded into grad_dens_pad afterwards
+    float4* quad = nullptr;
+    if (grad_dens_pad && (merge & 2)) {
+        quad = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + bwd_stash_bytes(N, S_h, S_w, P));
+        if (!aligned16(quad)) return fail(fn, "workspace must be 16-byte aligned");
+        if (cudaMemsetAsync(quad, 0, static_cast<size_t>(bwd_quad_bytes(V, D, H, W)), st) != cudaSuccess) return check_launch(fn);
+    }
+    const float4* dq = reinterpret_cast<const float4*>(dens_quad);
+    if ((merge & 1) && grad_feat_pad)
+        raymarch_bwd_kernel<true><<<grid, kBwThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, g_feat, g_sil, g_depth, grad_feat_pad,
+                                                               grad_dens_pad, grad_cam12, workspace, quad, D, H, W, S_h, S_w, P, tiles_x,
+                                                               interleave_views(V, D, H, W));
+    else
+        raymarch_bwd_kernel<false><<<grid, kBwThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, g_feat, g_sil, g_depth, grad_feat_pad,
+                                                                grad_dens_pad, grad_cam12, workspace, quad, D, H, W, S_h, S_w, P, tiles_x,
+                                                                interleave_views(V, D, H, W));
+    if (quad) {
+        const long long planes = static_cast<long long>(V) * (D + 2), total = planes * (H + 2) * (W + 2);
+        const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+        fold_dens_quads_kernel<<<blocks, 256, 0, st>>>(quad, grad_dens_pad, planes, H, W);
+    }
     return check_launch(fn);
 }

@@ -40,7 +40,7 @@ struct TmaMaps {
 };
 
 // kStages x kStageVox voxels (64 B each) of brick ring per CTA; two CTAs per SM
-template <int kStages, int kStageVox, int kWarpsY, bool kPrefetch = true>
+template <int kStages, int kStageVox, int kWarpsY, bool kPrefetch = true, bool kTuned = false>
 __global__ void __launch_bounds__(32 * (4 * kWarpsY + 1), kWarpsY <= 2 ? 2 : 1)
 raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __restrict__ feat_pad,
                         const float4* __restrict__ dens_quad,
@@ -187,7 +187,15 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
 
     // Software pipeline, one sample ahead: the footprint of sample k + 1 is computed and its density quad requested before
     // the feature work of sample k, so the global-load latency hides behind the 16 LDS.128 + 32 FFMA2 of the current sample.
+    const FootScale fs = {0.5f * static_cast<float>(W - 1), 0.5f * static_cast<float>(H - 1), 0.5f * static_cast<float>(D - 1)};
+    const float4* qvc = qv + (static_cast<long long>(1 + c) * Hq + 1) * Wq + 1;     // lane c's plane, border folded in
     auto fetch = [&](int kk, Foot& f, float4& d4) -> bool {     // footprint of sample kk + its density quad (lane c: plane z0 + c)
+        if (kTuned) {
+            f = sample_foot2(r, sm.zs[kk], fs, D, H, W);
+            const bool act = f.in && (kk >= r.k0) && (kk < r.k1);
+            if (act) d4 = __ldg(qvc + ((f.z0 * Hq + f.y0) * Wq + f.x0));             // 32-bit index inside one volume
+            return act;
+        }
         f = sample_foot(r, sm.zs[kk], D, H, W);
         const bool act = f.in && (kk >= r.k0) && (kk < r.k1);
         if (act) d4 = __ldg(qv + (static_cast<long long>(f.z0 + 1 + c) * Hq + (f.y0 + 1)) * Wq + (f.x0 + 1));
@@ -204,6 +212,8 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
         const SlabHeader h = sm.hdr[s & 7];
         const uint32_t brick = stage0 + static_cast<uint32_t>(st) * (kStageVox * 64);
         const int kend = min(h.kb, kw1);
+        // tuned: two samples per trip, so the one-ahead (footprint, quad) registers alternate instead of being copied
+#pragma unroll(kTuned ? 2 : 1)
         for (int k = max(h.ka, kw0); k < kend; ++k) {
             const float z = sm.zs[k];
             if (!kPrefetch) actn = fetch(k, fn, d4n);
@@ -232,7 +242,21 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
                 const bool inbox = (static_cast<unsigned>(xb) + 1u < static_cast<unsigned>(h.ex)) &&
                                    (static_cast<unsigned>(yb) + 1u < static_cast<unsigned>(h.ey)) &&
                                    (static_cast<unsigned>(zb) + 1u < static_cast<unsigned>(h.ez));
-                if (inbox) {
+                if (inbox && kTuned) {
+                    // one (dz, dy) corner row at a time: its 4 LDS.128 are issued back to back, then the 8 FFMA2 (the compiler's own
+                    // schedule kept 2 loads in flight per lane)
+                    const uint32_t a0 = brick + static_cast<uint32_t>(((zb * h.ey + yb) * h.ex + xb + c) << 6);
+                    const uint32_t sy = static_cast<uint32_t>(h.ex) << 6, sz = static_cast<uint32_t>(h.ex * h.ey) << 6;
+#pragma unroll
+                    for (int cn = 0; cn < 4; ++cn) {
+                        const uint32_t ap = a0 + ((cn & 2) ? sz : 0u) + ((cn & 1) ? sy : 0u);
+                        float4 v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = lds128(ap + choff[e]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) fma4(acc + 4 * e, cw[cn], v[e]);
+                    }
+                } else if (inbox) {
                     const uint32_t a0 = brick + static_cast<uint32_t>(((zb * h.ey + yb) * h.ex + xb + c) << 6);
                     const uint32_t sy = static_cast<uint32_t>(h.ex) << 6, sz = static_cast<uint32_t>(h.ex * h.ey) << 6;
 #pragma unroll
@@ -276,18 +300,18 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
     }
 }
 
-template <int kStages, int kStageVox, int kWarpsY, bool kPrefetch = true>
+template <int kStages, int kStageVox, int kWarpsY, bool kPrefetch = true, bool kTuned = false>
 static int tma_launch_cfg(const char* fn, const TmaMaps& maps, const float* feat_pad, const float4* dens_quad,
                           const int* view2vol, const float* cam12, const float* zs, float* out_feat, float* out_sil,
                           float* out_depth, int N, int V, int D, int H, int W, int S_h, int S_w, int P, cudaStream_t st) {
     constexpr int bytes = tma_smem_bytes(kStages, kStageVox), kTH = 4 * kWarpsY, threads = 32 * (4 * kWarpsY + 1);
     static_assert((kWarpsY <= 2 ? 2 : 1) * bytes <= 227 * 1024 && kStages <= kMaxStages, "the CTAs of an SM must fit");
     static_assert(kStageVox >= 16 * 16, "a stage must hold one plane of the largest shape");
-    if (int e = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(raymarch_fwd_tma_kernel<kStages, kStageVox, kWarpsY, kPrefetch>), bytes))
+    if (int e = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(raymarch_fwd_tma_kernel<kStages, kStageVox, kWarpsY, kPrefetch, kTuned>), bytes))
         return e;
     const int tiles_x = (S_w + kTW - 1) / kTW, tiles_y = (S_h + kTH - 1) / kTH;
     dim3 grid(tiles_x * tiles_y, N);
-    raymarch_fwd_tma_kernel<kStages, kStageVox, kWarpsY, kPrefetch><<<grid, threads, bytes, st>>>(
+    raymarch_fwd_tma_kernel<kStages, kStageVox, kWarpsY, kPrefetch, kTuned><<<grid, threads, bytes, st>>>(
         maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, D, H, W, S_h, S_w, P, tiles_x,
         interleave_views(V, D, H, W));
     return check_launch(fn);
@@ -302,7 +326,7 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
                             int V, int D, int H, int W, int S_h, int S_w, int P, cudaStream_t st) {
     static const int ring = [] {                // tuning knob (development): ring shape "stages x voxels per stage"
         const char* e = getenv("FORGE_K1T_RING");
-        return e ? atoi(e) : 2;
+        return e ? atoi(e) : 10;
     }();
     if (ring == 7)          // one lane per ray (raymarch_tma1.cu)
         return raymarch_fwd_tma1_launch(fn, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D, H, W, S_h,
@@ -329,12 +353,20 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
     if (ring == 9)          // no software pipelining of the density quad
         return tma_launch_cfg<2, 832, 2, false>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D,
                                                 H, W, S_h, S_w, P, st);
+    if (ring == 10)         // tuned instruction stream (A/B against the default)
+        return tma_launch_cfg<2, 880, 2, true, true>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V,
+                                                     D, H, W, S_h, S_w, P, st);
     if (ring == 3) FORGE_K1T(3, 552, 2);
     if (ring == 5) FORGE_K1T(2, 1700, 4);         // 16 x 16 pixel tile, one CTA per SM, twice the slab length
     if (ring == 6) FORGE_K1T(3, 1130, 4);
     if (ring == 1) FORGE_K1T(2, 832, 2);
-    FORGE_K1T(2, 880, 2);         // default: the largest stages two CTAs per SM can hold (0.347 vs 0.349 ms at cfg-2, 4.68 vs 4.73 ms at cfg-4)
+    if (ring == 2) FORGE_K1T(2, 880, 2);          // round-2 first default (untuned instruction stream)
 #undef FORGE_K1T
+    // default: the largest stages two CTAs per SM can hold (0.347 vs 0.349 ms at cfg-2, 4.68 vs 4.73 ms at cfg-4) with the tuned
+    // sample loop (folded un-normalisation, F2I + I2FP floor, 32-bit quad index, two samples per trip, 4 LDS.128 in flight):
+    // 0.348 -> 0.332 ms at cfg-2, 4.68 -> 4.49 ms at cfg-4
+    return tma_launch_cfg<2, 880, 2, true, true>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D,
+                                                 H, W, S_h, S_w, P, st);
 }
 
 }  // namespace forge

@@ -168,6 +168,68 @@ rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
     }
 }
 
+// Lean forward for C = 128 (the lifted feature volumes: 32 float4 per voxel = one voxel per warp instruction), round 2.
+// Same phases and the same arithmetic as rotate_fwd_kernel; what changes is the instruction stream of phase 2, which the
+// generic kernel spends mostly on index arithmetic (an integer division by the runtime channel count per item and eight
+// 64-bit multiply-adds: 130 SASS instructions per (voxel, float4), issue slots 54 % busy, ALU pipe 40 %): here a warp owns
+// whole voxels, the lane is the channel vector, corner offsets are premultiplied 32-bit float4 indices.
+template <int kShape, bool kStream>
+__global__ void __launch_bounds__(kRotThreads, 4)
+rotate_fwd_c128_kernel(const float4* __restrict__ in, const float* __restrict__ affine, const int* __restrict__ jobs,
+                       const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ gz,
+                       float inv_max, float4* __restrict__ out, int D, int H, int W, int tiles_x, int tiles_y) {
+    __shared__ __align__(16) RotTile s;
+    constexpr TileShape sh = tile_shape(kShape);
+    constexpr int kTx = sh.tx, kTy = sh.ty, kTz = sh.tz, kVox = kTx * kTy * kTz, kCU = 32;
+    const int m = blockIdx.y;
+    const RotJob job = {jobs[3 * m], jobs[3 * m + 1], jobs[3 * m + 2]};
+    const int tz = blockIdx.x / (tiles_x * tiles_y);
+    const int trem = blockIdx.x - tz * tiles_x * tiles_y;
+    const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    const long long vol = static_cast<long long>(D) * H * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4* src = in + static_cast<long long>(job.src) * vol * kCU + lane;
+    float4* dst = out + static_cast<long long>(job.dst) * vol * kCU + lane;
+
+    if (job.kind == 1) {   // view-0 passthrough (models/rotate.py:141)
+        for (int v = warp; v < kVox; v += kRotThreads / 32) {
+            const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
+            if (w >= W || h >= H || d >= D) continue;
+            const int o = ((d * H + h) * W + w) * kCU;
+            dst[o] = src[o];
+        }
+        return;
+    }
+    rotate_phase1(s, nullptr, affine, m, gx, gy, gz, inv_max, D, H, W, tx, ty, tz, sh);
+
+#pragma unroll 2
+    for (int v = warp; v < kVox; v += kRotThreads / 32) {
+        const int o = s.out[v];
+        if (o < 0) continue;
+        const int4 o0 = *reinterpret_cast<const int4*>(&s.off[v][0]), o1 = *reinterpret_cast<const int4*>(&s.off[v][4]);
+        const float4 w0 = *reinterpret_cast<const float4*>(&s.w[v][0]), w1 = *reinterpret_cast<const float4*>(&s.w[v][4]);
+        // one IMAD.WIDE.U32 per corner: lane base + voxel offset x 512 bytes
+        auto at = [&](int off) {
+            return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(src) +
+                                                         static_cast<unsigned long long>(static_cast<unsigned>(off)) * (kCU * 16ull)));
+        };
+        const float4 v0 = at(o0.x), v1 = at(o0.y), v2 = at(o0.z), v3 = at(o0.w), v4 = at(o1.x), v5 = at(o1.y), v6 = at(o1.z),
+                     v7 = at(o1.w);
+        float4 acc = vzero4();      // ATen accumulation order: x fastest, then y, then z
+        vfma(acc, v0, w0.x);
+        vfma(acc, v1, w0.y);
+        vfma(acc, v2, w0.z);
+        vfma(acc, v3, w0.w);
+        vfma(acc, v4, w1.x);
+        vfma(acc, v5, w1.y);
+        vfma(acc, v6, w1.z);
+        vfma(acc, v7, w1.w);
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<char*>(dst) + static_cast<unsigned long long>(static_cast<unsigned>(o)) * (kCU * 16ull));
+        if (kStream) __stcs(op, acc);       // written once, never re-read by this kernel: leave L2 to the source volumes
+        else *op = acc;
+    }
+}
+
 // ---- backward ------------------------------------------------------------------------------------
 __device__ __forceinline__ void vred(float* addr, float v) { atomicAdd(addr, v); }
 __device__ __forceinline__ void vred(float4* addr, const float4& v) { red_add_v4(reinterpret_cast<float*>(addr), v); }
@@ -321,7 +383,28 @@ extern "C" int forge_rotate_fwd(const float* vox_cl, const float* affine12, cons
     dim3 grid(tiles_x * tiles_y * tiles_z, M);
     const float inv_max = 1.0f / grid_coord_max;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (C % 4 == 0 && aligned16(vox_cl) && aligned16(out_cl)) {
+    static const bool lean = [] {
+        const char* e = getenv("FORGE_K2_LEAN");
+        return e ? atoi(e) != 0 : true;
+    }();
+    if (lean && C == 128 && (shape_id == 6 || shape_id == 7 || shape_id == 0) && aligned16(vox_cl) && aligned16(out_cl) &&
+        static_cast<long long>(D) * H * W * 32 < 2147483647LL) {
+        const float4* in4 = reinterpret_cast<const float4*>(vox_cl);
+        float4* out4 = reinterpret_cast<float4*>(out_cl);
+#define FORGE_K2_LEAN(SHAPE)                                                                                                    \
+    do {                                                                                                                        \
+        if (stream_st)                                                                                                          \
+            rotate_fwd_c128_kernel<SHAPE, true><<<grid, kRotThreads, 0, st>>>(in4, affine12, jobs, gx, gy, gz, inv_max, out4, D, H, W, \
+                                                                             tiles_x, tiles_y);                                 \
+        else                                                                                                                    \
+            rotate_fwd_c128_kernel<SHAPE, false><<<grid, kRotThreads, 0, st>>>(in4, affine12, jobs, gx, gy, gz, inv_max, out4, D, H, W, \
+                                                                              tiles_x, tiles_y);                                \
+    } while (0)
+        if (shape_id == 6) FORGE_K2_LEAN(6);
+        else if (shape_id == 7) FORGE_K2_LEAN(7);
+        else FORGE_K2_LEAN(0);
+#undef FORGE_K2_LEAN
+    } else if (C % 4 == 0 && aligned16(vox_cl) && aligned16(out_cl)) {
         const float4* in4 = reinterpret_cast<const float4*>(vox_cl);
         float4* out4 = reinterpret_cast<float4*>(out_cl);
 #define FORGE_K2_LAUNCH(SHAPE, STREAM)                                                                                  \

@@ -151,7 +151,7 @@ class _Raymarch(torch.autograd.Function):
         gf = gd = None
         if need_f or need_d or need_c:
             P = zs.numel()
-            ws = torch.empty(_lib.load().forge_raymarch_bwd_workspace(N, S_h, S_w, P) // 4, dtype=torch.float32, device=dev)
+            ws = torch.empty(_lib.load().forge_raymarch_bwd_workspace(N, V, D, H, W, S_h, S_w, P) // 4, dtype=torch.float32, device=dev)
             with torch.cuda.device(dev):
                 _lib.call("forge_raymarch_bwd", _ptr(feat_pad), _ptr(dens_quad), _ptr(view2vol), _ptr(cam12), _ptr(zs),
                           _ptr(g_out), _ptr(g_sil), _ptr(g_depth), _ptr(gfp), _ptr(gdp), _ptr(gc), _ptr(ws),

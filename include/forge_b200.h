@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FORGE_ABI_VERSION 17
+#define FORGE_ABI_VERSION 18
 #define FORGE_FEAT_CHANNELS 16 /* render feature channels (models/encoder.py:16-22 -> 16) */
 
 int forge_abi_version(void);
@@ -91,9 +91,9 @@ int forge_raymarch_bwd(const float* feat_pad, const float* dens_quad, const int*
                        const float* g_depth, float* grad_feat_pad, float* grad_dens_pad, float* grad_cam12,
                        float* workspace, int N, int V, int D, int H, int W, int S_h, int S_w, int P,
                        void* stream);
-/* Bytes of caller-owned scratch forge_raymarch_bwd needs (per-ray sigma_k, a_k, T_k between its two
- * passes; uninitialised is fine). */
-long long forge_raymarch_bwd_workspace(int N, int S_h, int S_w, int P);
+/* Bytes of caller-owned, 16-byte aligned scratch forge_raymarch_bwd needs (per-ray sigma_k, a_k, T_k between its two
+ * passes + the density gradient in dens_quad layout before it is folded into grad_dens_pad; uninitialised is fine). */
+long long forge_raymarch_bwd_workspace(int N, int V, int D, int H, int W, int S_h, int S_w, int P);
 
 /* ---- fused decoder ---------------------------------------------------------------------------
  * relu(conv_rgb(x)) of models/volume_render.py:29-37,73 for inference (BatchNorm in eval mode):

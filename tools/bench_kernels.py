@@ -109,6 +109,25 @@ def main():
             for entry in ("forge_raymarch_fwd_gather", "forge_raymarch_fwd_tma"):
                 ms, best = timeit(lambda: k1(entry), args.reps, flush)
                 report(entry, ms, best, k1_bytes, Mrays_per_s=round(rays / ms / 1e3, 1))
+        if want("k1bwd"):      # the backward kernel alone (C-ABI call, gradient buffers preallocated and accumulated into)
+            go = torch.randn(N, S, S, 16, device=DEV)
+            gs = torch.randn(N, S, S, device=DEV)
+            gfp = torch.zeros_like(fp)
+            gdp = torch.zeros(b, D + 2, D + 2, D + 2, device=DEV)
+            gc = torch.zeros_like(cam12)
+            ws = torch.empty(_lib.load().forge_raymarch_bwd_workspace(N, b, D, D, D, S, S, P) // 4, device=DEV)
+
+            def k1b(gf_, gd_, gc_):
+                _lib.call("forge_raymarch_bwd", fp.data_ptr(), dq.data_ptr(), inp['view2vol'].data_ptr(), cam12.data_ptr(),
+                          zs.data_ptr(), go.data_ptr(), gs.data_ptr(), gs.data_ptr(), gf_, gd_, gc_, ws.data_ptr(),
+                          N, b, D, D, D, S, S, P, torch.cuda.current_stream().cuda_stream)
+            for name, a in (("all gradients", (gfp.data_ptr(), gdp.data_ptr(), gc.data_ptr())),
+                            ("grad_feat + grad_cam", (gfp.data_ptr(), None, gc.data_ptr())),
+                            ("grad_dens + grad_cam", (None, gdp.data_ptr(), gc.data_ptr())),
+                            ("pose only", (None, None, gc.data_ptr()))):
+                ms, best = timeit(lambda: k1b(*a), args.reps, flush)
+                report("raymarch_bwd kernel, " + name, ms, best, None, Mrays_per_s=round(rays / ms / 1e3, 1),
+                       merge=os.environ.get("FORGE_K1B_MERGE", "default"))
         if want("volrender"):
             def full():
                 cam = dict(R=inp['R'], T=inp['T'], K=inp['K'].clone())
@@ -191,6 +210,14 @@ def main():
             report("Rotate_world.forward channels-last in/out (kernel + torch pose glue)", ms, best, k2_bytes)
             ms, best = timeit(lambda: rot(vox, poses, grid_size=n), args.reps, flush)
             report("Rotate_world.forward NCDHW in (+relayout kernel)", ms, best, k2_bytes)
+            # transform jobs only (view 0 aliased): SURVEY 8d's numerator, what bench.py's roofline_rotate times
+            jobs_t = rot._jobs_aliased(b, t, DEV, None)
+            out_t = torch.empty(b * (t - 1), n, n, n, C, device=DEV)
+            ms, best = timeit(lambda: _lib.call("forge_rotate_fwd", vcl.data_ptr(), A.data_ptr(), jobs_t.data_ptr(), gxd.data_ptr(),
+                                                gyd.data_ptr(), gzd.data_ptr(), float(gmax), out_t.data_ptr(), b * (t - 1), C, n, n, n,
+                                                torch.cuda.current_stream().cuda_stream), args.reps, flush)
+            report("rotate_fwd kernel, %d transform jobs only" % (b * (t - 1)), ms, best, 2 * b * (t - 1) * C * n ** 3 * 4,
+                   knobs={k: os.environ.get(k) for k in ("FORGE_K2_LEAN", "FORGE_K2_SHAPE", "FORGE_K2_STREAM")})
             if args.ref:
                 from oracle import reference_path as rp
                 ms, best = timeit(lambda: rp.rotate_world_forward(vox, poses, n, 1.0), max(3, args.reps // 4), flush)
