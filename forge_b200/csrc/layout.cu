@@ -177,8 +177,8 @@ __global__ void sample_points_kernel(const float* __restrict__ pts, int M, int D
 // channels-last rows [W+2][16] plus the density-quad rows [W+1][4].  HBM-bound: reads V*17*D*H*W*4 bytes,
 // writes ~1.1x that + 4x the density.
 constexpr int kPackThreads = 256;
-constexpr int kPackRows = 8;
 
+template <int kPackRows>
 __global__ void __launch_bounds__(kPackThreads)
 pack_volume_kernel(const float* __restrict__ feat, int feat_cl, const float* __restrict__ dens,
                    float* __restrict__ feat_pad, float4* __restrict__ dens_quad, int D, int H, int W, int ygroups) {
@@ -339,13 +339,28 @@ extern "C" int forge_pack_volume(const float* feat, int feat_channels_last, cons
     if (V > 65535) return fail(fn, "more than 65535 volumes in one launch");
     if (!aligned16(dens_quad)) return fail(fn, "dens_quad must be 16-byte aligned");
     if (!aligned16(feat_pad) || (feat_channels_last && !aligned16(feat))) return fail(fn, "feat_pad / feat must be 16-byte aligned");
-    const size_t smem = sizeof(float) * (kPackRows * (W * 17 + 2) + (kPackRows + 1) * (W + 2));
+    static const int rows_env = [] {        // tuning knob (development): padded y-rows per CTA
+        const char* e = getenv("FORGE_PACK_ROWS");
+        return e ? atoi(e) : 0;
+    }();
+    // ~37 KB of shared memory per CTA (6 CTAs per SM) is the sweet spot: 8 rows up to W = 64, 4 rows beyond (measured on B200:
+    // cfg-2 W = 64: 4 / 8 / 16 rows = 0.046 / 0.044 / 0.058 ms; cfg-4 W = 128: 0.511 / 0.683 / 1.554 ms = 76 / 57 / 25 % of the HBM peak)
+    const int rows = (rows_env == 4 || rows_env == 8 || rows_env == 16) ? rows_env : (W > 64 ? 4 : 8);
+    const size_t smem = sizeof(float) * (rows * (W * 17 + 2) + (rows + 1) * (W + 2));
     if (smem > 200 * 1024) return fail(fn, "volume rows longer than 360 voxels are not supported");
-    if (int rc = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(pack_volume_kernel), smem)) return rc;
-    const int ygroups = (H + 2 + kPackRows - 1) / kPackRows;
+    const int ygroups = (H + 2 + rows - 1) / rows;
     dim3 grid((D + 2) * ygroups, V);
-    pack_volume_kernel<<<grid, kPackThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        feat, feat_channels_last, dens, feat_pad, reinterpret_cast<float4*>(dens_quad), D, H, W, ygroups);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float4* dq = reinterpret_cast<float4*>(dens_quad);
+#define FORGE_PACK(R)                                                                                                  \
+    do {                                                                                                               \
+        if (int rc = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(pack_volume_kernel<R>), smem)) return rc;   \
+        pack_volume_kernel<R><<<grid, kPackThreads, smem, st>>>(feat, feat_channels_last, dens, feat_pad, dq, D, H, W, ygroups); \
+    } while (0)
+    if (rows == 4) FORGE_PACK(4);
+    else if (rows == 16) FORGE_PACK(16);
+    else FORGE_PACK(8);
+#undef FORGE_PACK
     return check_launch(fn);
 }
 

@@ -262,9 +262,11 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
             for (int cn = 0; cn < 8; ++cn) {
                 const int o = off + ((cn & 4) ? row_z : 0) + ((cn & 2) ? row_y : 0) + ((cn & 1) ? 16 : 0);
                 const f8 val = ldg256(fv + o);
-                float qd = gF[0] * val.v[0];
+                // g_F . f over 8 channels as packed FFMA2 on channel pairs
+                float2 q2 = __ffma2_rn(make_float2(gF[0], gF[1]), make_float2(val.v[0], val.v[1]), make_float2(0.f, 0.f));
 #pragma unroll
-                for (int e = 1; e < 8; ++e) qd = fmaf(gF[e], val.v[e], qd);
+                for (int e = 1; e < 4; ++e) q2 = __ffma2_rn(make_float2(gF[2 * e], gF[2 * e + 1]), make_float2(val.v[2 * e], val.v[2 * e + 1]), q2);
+                const float qd = q2.x + q2.y;
                 const float wx = (cn & 1) ? f.wx1 : f.wx0, wy = (cn & 2) ? f.wy1 : f.wy0, wz = (cn & 4) ? f.wz1 : f.wz0;
                 const float wxy = (cn & 2) ? ((cn & 1) ? w11 : w01) : ((cn & 1) ? w10 : w00);
                 const float w = wxy * wz;
@@ -287,35 +289,39 @@ raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict
             if (scat) *reinterpret_cast<float4*>(&cws[ray * 8 + 4 * c]) = make_float4(cwv[0], cwv[1], cwv[2], cwv[3]);
             const unsigned grp = __match_any_sync(0xffffffffu, scat ? off : ~lane);      // lanes (ray pairs) with the same base voxel
             __syncwarp();
-            if (scat && (lane >> 1) == ((__ffs(grp) - 1) >> 1)) {       // leader pair of the group: lane c adds its 4 + 4 channels
-                const unsigned members = grp & 0x55555555u;              // one bit per member ray
+            // The first two member rays of a group take one z-plane of corners each (a lone ray takes both, one after the other), so
+            // the warp spends ~group size iterations instead of twice that with the rest of the group idle.
+            const unsigned members = grp & 0x55555555u;                  // one bit per member ray
+            const int gsize = __popc(members), rank = __popc(members & ((1u << (lane & 30)) - 1u));
+            auto reduce_plane = [&](int hz) {                            // sum the group's contributions to the 4 corners of plane dz = hz
+                float2 a[4][2], b[4][2];                                 // [corner][channel pair]: lane c owns channels 4c.. and 8 + 4c..
 #pragma unroll
-                for (int hz = 0; hz < 2; ++hz) {
-                    float4 a[4], b[4];
+                for (int e = 0; e < 4; ++e) a[e][0] = a[e][1] = b[e][0] = b[e][1] = make_float2(0.f, 0.f);
+                for (unsigned rr = members; rr; rr &= rr - 1) {
+                    const int mray = (warp * 32 + __ffs(rr) - 1) >> 1;
+                    const float4 w4 = *reinterpret_cast<const float4*>(&cws[mray * 8 + 4 * hz]);
+                    const float4 ga = *reinterpret_cast<const float4*>(&gFs[(mray * 2 + c) * 8]);
+                    const float4 gb = *reinterpret_cast<const float4*>(&gFs[(mray * 2 + c) * 8 + 4]);
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) a[e] = b[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (unsigned rr = members; rr; rr &= rr - 1) {
-                        const int mray = (warp * 32 + __ffs(rr) - 1) >> 1;
-                        const float4 w4 = *reinterpret_cast<const float4*>(&cws[mray * 8 + 4 * hz]);
-                        const float4 ga = *reinterpret_cast<const float4*>(&gFs[(mray * 2 + c) * 8]);
-                        const float4 gb = *reinterpret_cast<const float4*>(&gFs[(mray * 2 + c) * 8 + 4]);
-                        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            a[e].x = fmaf(wv[e], ga.x, a[e].x), a[e].y = fmaf(wv[e], ga.y, a[e].y);
-                            a[e].z = fmaf(wv[e], ga.z, a[e].z), a[e].w = fmaf(wv[e], ga.w, a[e].w);
-                            b[e].x = fmaf(wv[e], gb.x, b[e].x), b[e].y = fmaf(wv[e], gb.y, b[e].y);
-                            b[e].z = fmaf(wv[e], gb.z, b[e].z), b[e].w = fmaf(wv[e], gb.w, b[e].w);
-                        }
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int o = off + (hz ? row_z : 0) + ((e & 2) ? row_y : 0) + ((e & 1) ? 16 : 0);
-                        red_add_v4(gfs + o, a[e]);
-                        red_add_v4(gfs + o + 8, b[e]);
+                    for (int e = 0; e < 4; ++e) {                        // packed FFMA2: two channels per instruction
+                        const float2 w2 = make_float2(wv[e], wv[e]);
+                        a[e][0] = __ffma2_rn(w2, make_float2(ga.x, ga.y), a[e][0]);
+                        a[e][1] = __ffma2_rn(w2, make_float2(ga.z, ga.w), a[e][1]);
+                        b[e][0] = __ffma2_rn(w2, make_float2(gb.x, gb.y), b[e][0]);
+                        b[e][1] = __ffma2_rn(w2, make_float2(gb.z, gb.w), b[e][1]);
                     }
                 }
-            }
+                const int oz = off + (hz ? row_z : 0);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int o = oz + ((e & 2) ? row_y : 0) + ((e & 1) ? 16 : 0);
+                    red_add_v4(gfs + o, make_float4(a[e][0].x, a[e][0].y, a[e][1].x, a[e][1].y));
+                    red_add_v4(gfs + o + 8, make_float4(b[e][0].x, b[e][0].y, b[e][1].x, b[e][1].y));
+                }
+            };
+            if (scat && rank < 2) reduce_plane(rank);
+            if (scat && gsize == 1) reduce_plane(1);
         }
         a_part += __shfl_xor_sync(0xffffffffu, a_part, 1);
         if (act) {
