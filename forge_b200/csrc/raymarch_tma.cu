@@ -48,7 +48,11 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
                         float* __restrict__ out_feat, float* __restrict__ out_sil, float* __restrict__ out_depth, int D,
                         int H, int W, int Sh, int Sw, int P, int tiles_x, int interleave) {
     constexpr int kConsWarps = 4 * kWarpsY, kTmaThreads = 32 * (kConsWarps + 1), kTH = 4 * kWarpsY;
-    constexpr bool kTuned = kMode >= 1;          // 0: first round-2 sample loop, 1: tuned instruction stream, 2: sample-pair mapping
+    constexpr bool kTuned = kMode >= 1;          // 0: first round-2 sample loop, 1: tuned instruction stream
+    // (A sample-pair mapping -- lane c takes sample k + c and reads all 8 corners, so the footprint / density / weight work is done
+    // once per ray-sample instead of once per lane -- was built and measured in commit "K1-T sample-pair mapping": same instruction
+    // count, 20 more live registers under the 96-register cap of 2 x 9 warps, 51 M local-memory sectors of spill traffic through L1:
+    // 0.556 vs 0.333 ms.  profiles/r02_k1t_pair.txt)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw + kStages * kStageVox * 64);
     const uint32_t stage0 = smem_u32(smem_raw);
@@ -171,138 +175,6 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
             mbar_wait(&sm.empty[s % kStages], ((s / kStages) & 1) ^ 1);
             issue(s);
             plan(s + 1, sm.hdr[s & 7].kb);
-        }
-        return;
-    }
-
-    if constexpr (kMode == 2) {
-        // ================= consumers, SAMPLE-PAIR mapping =================
-        // The two lanes of a ray take alternate samples (lane c: k_pair + c) and each reads all 8 corners of its own sample,
-        // instead of both lanes walking every sample and splitting the x-corners: the per-sample scalar work (footprint, density,
-        // weights, addresses: ~150 of the ~200 instructions per sample) is done once per ray-sample instead of twice.  The
-        // transmittance recurrence needs one shuffle per pair (the partner's sigma), as before.  Bank pairing: box pitches are
-        // even, so the parity of a corner's record index is (base + dx) & 1; lane c visits first the x-corner whose record has
-        // parity c, so the two lanes of a pair always read opposite 64-byte halves and the 8 lanes of an LDS.128 phase stay on 8
-        // distinct 4-bank groups (same chunk rotation by the ray's index in its quarter-warp).
-        const float4* qv = dens_quad + v * (D + 2) * Hq * Wq + (static_cast<long long>(Hq) + 1) * Wq + 1;    // border folded in
-        const int plane_q = Hq * Wq;
-        const int row_y = Wp * 16, row_z = Hp * Wp * 16;
-        const FootScale fs = {0.5f * static_cast<float>(W - 1), 0.5f * static_cast<float>(H - 1), 0.5f * static_cast<float>(D - 1)};
-        uint32_t choff[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) choff[e] = static_cast<uint32_t>((e ^ rq) << 4);
-        float acc[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-        float T = 1.f, depth = 0.f;
-
-        Foot fn;                                            // this lane's next sample, fetched one pair ahead
-        float4 dna = make_float4(0.f, 0.f, 0.f, 0.f), dnb = dna;
-        bool actn = false;
-        auto fetch = [&](int kk) {
-            actn = false;
-            if (kk < kw1) {
-                fn = sample_foot2(r, sm.zs[kk], fs, D, H, W);
-                actn = fn.in && (kk >= r.k0) && (kk < r.k1);
-                if (actn) {
-                    const float4* q = qv + ((fn.z0 * Hq + fn.y0) * Wq + fn.x0);
-                    dna = __ldg(q);
-                    dnb = __ldg(q + plane_q);
-                }
-            }
-        };
-        if (kw1 > kw0) fetch(kw0 + c);
-
-        for (int s = 0;; ++s) {
-            const int st = s % kStages;
-            mbar_wait(&sm.full[st], (s / kStages) & 1);
-            const SlabHeader h = sm.hdr[s & 7];
-            const uint32_t brick = stage0 + static_cast<uint32_t>(st) * (kStageVox * 64);
-            const uint32_t sy = static_cast<uint32_t>(h.ex) << 6, sz = static_cast<uint32_t>(h.ex * h.ey) << 6;
-            const int kend = min(h.kb, kw1);
-            for (int kp = max(h.ka, kw0); kp < kend; kp += 2) {
-                const int k = kp + c;
-                const Foot f = fn;
-                const float4 da = dna, db = dnb;
-                const bool act = actn && (k < kend);       // the fetched sample is always sample k (pairs tile the slabs in order)
-                fetch((kp + 2 < kend ? kp + 2 : h.kb) + c);
-                float sg = 0.f;
-                float w00 = 0.f, w10 = 0.f, w01 = 0.f, w11 = 0.f;
-                if (act) {          // both density planes of the own sample (same operation order as the two-lane split: part0 + part1)
-                    w00 = __fmul_rn(f.wx0, f.wy0), w10 = __fmul_rn(f.wx1, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1), w11 = __fmul_rn(f.wx1, f.wy1);
-                    float p0 = __fmul_rn(w00, f.wz0) * da.x;
-                    p0 = fmaf(__fmul_rn(w10, f.wz0), da.y, p0);
-                    p0 = fmaf(__fmul_rn(w01, f.wz0), da.z, p0);
-                    p0 = fmaf(__fmul_rn(w11, f.wz0), da.w, p0);
-                    float p1 = __fmul_rn(w00, f.wz1) * db.x;
-                    p1 = fmaf(__fmul_rn(w10, f.wz1), db.y, p1);
-                    p1 = fmaf(__fmul_rn(w01, f.wz1), db.z, p1);
-                    p1 = fmaf(__fmul_rn(w11, f.wz1), db.w, p1);
-                    sg = p0 + p1;
-                }
-                const float so = __shfl_xor_sync(0xffffffffu, sg, 1);
-                const float s0 = c ? so : sg, s1 = c ? sg : so;        // sigma of sample kp, kp + 1
-                const float T1 = T * (1.f - s0);
-                const float wk = c ? s1 * T1 : s0 * T;
-                T = T1 * (1.f - s1);
-                if (wk != 0.f) {    // sigma != 0 implies act
-                    const int xb = f.x0 + 1 - h.lx, yb = f.y0 + 1 - h.ly, zb = f.z0 + 1 - h.lz;
-                    const bool inbox = (static_cast<unsigned>(xb) + 1u < static_cast<unsigned>(h.ex)) &&
-                                       (static_cast<unsigned>(yb) + 1u < static_cast<unsigned>(h.ey)) &&
-                                       (static_cast<unsigned>(zb) + 1u < static_cast<unsigned>(h.ez));
-                    const int rec = (zb * h.ey + yb) * h.ex + xb;               // brick record of corner (0, 0, 0)
-                    const int flip = inbox ? ((rec ^ c) & 1) : 0;               // dx visited first
-                    // (wx wy) of the first / second visited x-corner for dy = 0, 1 -- ATen's order (wx wy) wz
-                    const float wa0 = flip ? w10 : w00, wa1 = flip ? w11 : w01, wb0 = flip ? w00 : w10, wb1 = flip ? w01 : w11;
-                    const float wkz0 = 0.f;      // (weights are formed per visit: fewer live registers across the LDS block)
-                    (void)wkz0;
-                    if (inbox) {
-                        // records are 64-byte aligned: chunk (e ^ rq) sits at (record + 16 rq) ^ 16 e
-                        const uint32_t a0 = brick + (static_cast<uint32_t>(rec) << 6) + choff[0];
-#pragma unroll
-                        for (int cn = 0; cn < 8; ++cn) {         // cn = xs * 4 + dz * 2 + dy
-                            const uint32_t ap = a0 + (((cn >> 2) ^ flip) ? 64u : 0u) + ((cn & 2) ? sz : 0u) + ((cn & 1) ? sy : 0u);
-                            float4 vv[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) vv[e] = lds128(ap ^ static_cast<uint32_t>(e << 4));
-#pragma unroll
-                            const float cwv = wk * __fmul_rn((cn >> 2) ? ((cn & 1) ? wb1 : wb0) : ((cn & 1) ? wa1 : wa0), (cn & 2) ? f.wz1 : f.wz0);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) fma4(acc + 4 * e, cwv, vv[e]);
-                        }
-                    } else {
-                        const float* p = fvol + ((f.z0 + 1) * Hp + (f.y0 + 1)) * row_y + (f.x0 + 1) * 16;
-#pragma unroll
-                        for (int cn = 0; cn < 8; ++cn) {
-                            const float* pc = p + ((cn >> 2) ? 16 : 0) + ((cn & 2) ? row_z : 0) + ((cn & 1) ? row_y : 0);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                fma4(acc + 4 * e, wk * __fmul_rn((cn >> 2) ? ((cn & 1) ? wb1 : wb0) : ((cn & 1) ? wa1 : wa0), (cn & 2) ? f.wz1 : f.wz0),
-                                     ldg128(pc + (choff[e] >> 2)));
-                        }
-                    }
-                    depth = fmaf(wk, sm.zs[k], depth);
-                }
-            }
-            if (h.kb >= kt1) break;                               // that was the last slab
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[st]);            // release the stage to the producer
-        }
-        // ---- combine the even / odd sample halves of the pair, store (acc[4 e + t] is channel 4 (e ^ rq) + t) ----
-#pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
-        depth += __shfl_xor_sync(0xffffffffu, depth, 1);
-        if (valid) {
-            const long long pix = (static_cast<long long>(n) * Sh + i) * Sw + j;
-            float* o = out_feat + pix * 16;
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if ((e >> 1) == c)
-                    *reinterpret_cast<float4*>(o + (choff[e] >> 2)) = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
-            if (c == 0) {
-                out_sil[pix] = 1.f - T;
-                if (out_depth) out_depth[pix] = depth;
-            }
         }
         return;
     }
@@ -489,9 +361,6 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
     if (ring == 10)         // tuned instruction stream (A/B against the default)
         return tma_launch_cfg<2, 880, 2, true, 1>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V,
                                                      D, H, W, S_h, S_w, P, st);
-    if (ring == 11)         // sample-pair mapping
-        return tma_launch_cfg<2, 880, 2, true, 2>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V,
-                                                  D, H, W, S_h, S_w, P, st);
     if (ring == 3) FORGE_K1T(3, 552, 2);
     if (ring == 5) FORGE_K1T(2, 1700, 4);         // 16 x 16 pixel tile, one CTA per SM, twice the slab length
     if (ring == 6) FORGE_K1T(3, 1130, 4);

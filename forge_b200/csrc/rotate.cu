@@ -145,6 +145,10 @@ rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
         const int v = e / CU, cu = e - v * CU;
         const int o = s.out[v];
         if (o < 0) continue;
+        if (s.mask[v] == 0u) {              // the sample lies outside the source volume (zeros padding): nothing to read
+            dst[static_cast<long long>(o) * CU + cu] = vzero<VecT>();
+            continue;
+        }
         const int4 o0 = *reinterpret_cast<const int4*>(&s.off[v][0]), o1 = *reinterpret_cast<const int4*>(&s.off[v][4]);
         const float4 w0 = *reinterpret_cast<const float4*>(&s.w[v][0]), w1 = *reinterpret_cast<const float4*>(&s.w[v][4]);
         const VecT* p = src + cu;
@@ -174,7 +178,7 @@ rotate_fwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
 // 64-bit multiply-adds: 130 SASS instructions per (voxel, float4), issue slots 54 % busy, ALU pipe 40 %): here a warp owns
 // whole voxels, the lane is the channel vector, corner offsets are premultiplied 32-bit float4 indices.
 template <int kShape, bool kStream>
-__global__ void __launch_bounds__(kRotThreads, 4)
+__global__ void __launch_bounds__(kRotThreads, 4)       // 5 / 6 CTAs per SM (48 / 40 registers) measured: 0.1157 / 0.1188 vs 0.1147 ms
 rotate_fwd_c128_kernel(const float4* __restrict__ in, const float* __restrict__ affine, const int* __restrict__ jobs,
                        const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ gz,
                        float inv_max, float4* __restrict__ out, int D, int H, int W, int tiles_x, int tiles_y) {
@@ -206,6 +210,12 @@ rotate_fwd_c128_kernel(const float4* __restrict__ in, const float* __restrict__ 
     for (int v = warp; v < kVox; v += kRotThreads / 32) {
         const int o = s.out[v];
         if (o < 0) continue;
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<char*>(dst) + static_cast<unsigned long long>(static_cast<unsigned>(o)) * (kCU * 16ull));
+        if (s.mask[v] == 0u) {              // the sample lies outside the source volume (zeros padding): nothing to read
+            if (kStream) __stcs(op, vzero4());
+            else *op = vzero4();
+            continue;
+        }
         const int4 o0 = *reinterpret_cast<const int4*>(&s.off[v][0]), o1 = *reinterpret_cast<const int4*>(&s.off[v][4]);
         const float4 w0 = *reinterpret_cast<const float4*>(&s.w[v][0]), w1 = *reinterpret_cast<const float4*>(&s.w[v][4]);
         // one IMAD.WIDE.U32 per corner: lane base + voxel offset x 512 bytes
@@ -224,7 +234,6 @@ rotate_fwd_c128_kernel(const float4* __restrict__ in, const float* __restrict__ 
         vfma(acc, v5, w1.y);
         vfma(acc, v6, w1.z);
         vfma(acc, v7, w1.w);
-        float4* op = reinterpret_cast<float4*>(reinterpret_cast<char*>(dst) + static_cast<unsigned long long>(static_cast<unsigned>(o)) * (kCU * 16ull));
         if (kStream) __stcs(op, acc);       // written once, never re-read by this kernel: leave L2 to the source volumes
         else *op = acc;
     }
@@ -289,8 +298,9 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
         const int v = e / CU, cu = e - v * CU;
         const int o = s.out[v];
         if (o < 0) continue;
-        const VecT g = go[static_cast<long long>(o) * CU + cu];
         const unsigned mask = s.mask[v];
+        if (mask == 0u) continue;           // sample outside the source volume: no gradient to anything
+        const VecT g = go[static_cast<long long>(o) * CU + cu];
         float gix = 0.f, giy = 0.f, giz = 0.f;
 #pragma unroll
         for (int cn = 0; cn < 8; ++cn) {

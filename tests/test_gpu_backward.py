@@ -69,6 +69,51 @@ def test_raymarch_gradients_vs_oracle(dense):
     assert _rel(K0.grad[:, :2], gK_ref[:, :2]) <= RTOL
 
 
+@pytest.mark.parametrize("n_obj,n_views,img,vol,P,dense", [
+    (1, 5, 128, 32, 32, False),       # cfg-1 sizes: 4x4-ray patches spread over ~6-7 base voxels (the merged scatter's common case)
+    (1, 2, 70, 20, 33, True),         # partial tiles in both directions, odd sample count, sigma > 1
+    (1, 2, 256, 16, 24, False),       # 128^2 rays over a 16^3 volume: whole warps share one base voxel (group size 16)
+])
+def test_raymarch_gradients_vs_oracle_merge_patterns(n_obj, n_views, img, vol, P, dense):
+    """K1 backward pre-reduces, per warp and sample, the feature-gradient contributions of rays that share a base voxel
+    (raymarch.cu, kMerge) and accumulates the density gradient as quads: group sizes from 1 to 16 against the fp64 oracle."""
+    inp, S, g_out, g_sil, g_dep = _render_case(n_obj, n_views, img, vol, P, dense, seed=11)
+    gf_ref, gd_ref, gR_ref, gT_ref, _ = _oracle_grads(inp, S, P, g_out, g_sil, g_dep, img)
+    m = VolRender(syn.make_config(img_size=img, n_pts_per_ray=P)).to(DEV)
+    feat = inp['feat'].to(DEV).requires_grad_(True)
+    dens = inp['dens'].to(DEV).requires_grad_(True)
+    R = inp['R'].to(DEV).requires_grad_(True)
+    T = inp['T'].to(DEV).requires_grad_(True)
+    cam = dict(R=R, T=T, K=inp['K'].to(DEV) * 1.0)
+    f, o, d, _, _, _ = m.render_features(cam, feat, dens, True, view2vol=inp['view2vol'])
+    ((f * g_out.to(DEV)).sum() + (o * g_sil.to(DEV)).sum() + (d * g_dep.to(DEV)).sum()).backward()
+    assert _rel(feat.grad, gf_ref) <= RTOL
+    assert _rel(dens.grad, gd_ref) <= RTOL
+    assert _rel(R.grad, gR_ref) <= RTOL
+    assert _rel(T.grad, gT_ref) <= RTOL
+
+
+def test_raymarch_backward_non_cubic_volume_and_missing_rays():
+    """D != H != W (quad / padded strides differ per axis) and a camera that misses the volume entirely."""
+    img, P = 64, 24
+    inp, S, g_out, g_sil, g_dep = _render_case(1, 3, img, 12, P, False, seed=13)
+    g = torch.Generator().manual_seed(4)
+    inp['feat'] = torch.randn(1, 16, 10, 14, 18, generator=g)
+    inp['dens'] = 0.3 * torch.rand(1, 1, 10, 14, 18, generator=g)
+    inp['T'][2] = torch.tensor([3.0, 0.0, 1.5])
+    gf_ref, gd_ref, _, gT_ref, _ = _oracle_grads(inp, S, P, g_out, g_sil, g_dep, img)
+    m = VolRender(syn.make_config(img_size=img, n_pts_per_ray=P)).to(DEV)
+    feat = inp['feat'].to(DEV).requires_grad_(True)
+    dens = inp['dens'].to(DEV).requires_grad_(True)
+    T = inp['T'].to(DEV).requires_grad_(True)
+    cam = dict(R=inp['R'].to(DEV), T=T, K=inp['K'].to(DEV) * 1.0)
+    f, o, d, _, _, _ = m.render_features(cam, feat, dens, True, view2vol=inp['view2vol'])
+    ((f * g_out.to(DEV)).sum() + (o * g_sil.to(DEV)).sum() + (d * g_dep.to(DEV)).sum()).backward()
+    assert _rel(feat.grad, gf_ref) <= RTOL
+    assert _rel(dens.grad, gd_ref) <= RTOL
+    assert _rel(T.grad, gT_ref) <= RTOL
+
+
 def test_raymarch_pose_only_backward_matches_full():
     """Detached volumes (test-time pose refinement, reference kubric_eval.py:405,450-504): the
     volume scatters are skipped and the camera gradient is unchanged."""
