@@ -73,11 +73,20 @@ struct RotTile {
     float A[12];
 };
 
+// Compact per-voxel records of the lean forward kernel: two broadcast LDS.128 per voxel instead of six (output index, mask, 8
+// offsets, 8 weights) -- the kernel is bound by L1 data-pipe wavefronts (ncu: 85 % of peak), and those reads were 6 of its 42 per
+// voxel.  cls: 0 = sample outside the source volume, 1 = all 8 corners inside (offsets are base + fixed strides, weights are
+// formed in registers with ATen's (wx wy) wz order), 2 = partly outside (the full tables of RotTile are used).
+struct RotLean {
+    int4 rec[kTileVox];        // {output voxel index or -1, base voxel offset | cls << 30, wx0, wx1}
+    float4 wts[kTileVox];      // {wy0, wy1, wz0, wz1}
+};
+
 // phase 1 shared by forward and backward; optionally keeps the per-axis weights for d out/d pos
 __device__ __forceinline__ void rotate_phase1(RotTile& s, float (*frac)[6], const float* __restrict__ affine, int m,
                                               const float* __restrict__ gx, const float* __restrict__ gy,
                                               const float* __restrict__ gz, float inv_max, int D, int H, int W,
-                                              int tx, int ty, int tz, const TileShape sh) {
+                                              int tx, int ty, int tz, const TileShape sh, RotLean* lean = nullptr) {
     const int kTx = sh.tx, kTy = sh.ty, kTz = sh.tz;
     if (threadIdx.x < 12) s.A[threadIdx.x] = affine[12 * m + threadIdx.x];
     __syncthreads();
@@ -85,6 +94,7 @@ __device__ __forceinline__ void rotate_phase1(RotTile& s, float (*frac)[6], cons
     const int w = tx * kTx + (v % kTx), h = ty * kTy + ((v / kTx) % kTy), d = tz * kTz + v / (kTx * kTy);
     if (v >= kTx * kTy * kTz || w >= W || h >= H || d >= D) {     // half tiles leave the upper threads without a voxel
         s.out[v] = -1;
+        if (lean) lean->rec[v] = make_int4(-1, 0, 0, 0);
     } else {
         s.out[v] = (d * H + h) * W + w;
         const Tri t = rotate_tri(s.A, gx[w], gy[h], gz[d], inv_max, D, H, W);
@@ -96,6 +106,12 @@ __device__ __forceinline__ void rotate_phase1(RotTile& s, float (*frac)[6], cons
                       z = min(max(t.z0 + (cn >> 2), 0), D - 1);
             s.off[v][cn] = (z * H + y) * W + x;
             s.w[v][cn] = in ? tri_weight(t, cn) : 0.f;
+        }
+        if (lean) {
+            const int cls = t.mask == 0u ? 0 : (t.mask == 0xffu ? 1 : 2);
+            const int base = cls == 1 ? (t.z0 * H + t.y0) * W + t.x0 : 0;
+            lean->rec[v] = make_int4(s.out[v], base | (cls << 30), __float_as_int(t.wx0), __float_as_int(t.wx1));
+            lean->wts[v] = make_float4(t.wy0, t.wy1, t.wz0, t.wz1);
         }
         if (frac) {
             frac[v][0] = t.wx0;
@@ -204,36 +220,53 @@ rotate_fwd_c128_kernel(const float4* __restrict__ in, const float* __restrict__ 
         }
         return;
     }
-    rotate_phase1(s, nullptr, affine, m, gx, gy, gz, inv_max, D, H, W, tx, ty, tz, sh);
+    __shared__ __align__(16) RotLean sl;
+    rotate_phase1(s, nullptr, affine, m, gx, gy, gz, inv_max, D, H, W, tx, ty, tz, sh, &sl);
+    constexpr unsigned long long kVoxBytes = kCU * 16ull;
+    const unsigned long long sy_b = static_cast<unsigned long long>(W) * kVoxBytes, sz_b = static_cast<unsigned long long>(H) * sy_b;
 
 #pragma unroll 2
     for (int v = warp; v < kVox; v += kRotThreads / 32) {
-        const int o = s.out[v];
-        if (o < 0) continue;
-        float4* op = reinterpret_cast<float4*>(reinterpret_cast<char*>(dst) + static_cast<unsigned long long>(static_cast<unsigned>(o)) * (kCU * 16ull));
-        if (s.mask[v] == 0u) {              // the sample lies outside the source volume (zeros padding): nothing to read
-            if (kStream) __stcs(op, vzero4());
-            else *op = vzero4();
-            continue;
-        }
-        const int4 o0 = *reinterpret_cast<const int4*>(&s.off[v][0]), o1 = *reinterpret_cast<const int4*>(&s.off[v][4]);
-        const float4 w0 = *reinterpret_cast<const float4*>(&s.w[v][0]), w1 = *reinterpret_cast<const float4*>(&s.w[v][4]);
-        // one IMAD.WIDE.U32 per corner: lane base + voxel offset x 512 bytes
-        auto at = [&](int off) {
-            return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(src) +
-                                                         static_cast<unsigned long long>(static_cast<unsigned>(off)) * (kCU * 16ull)));
-        };
-        const float4 v0 = at(o0.x), v1 = at(o0.y), v2 = at(o0.z), v3 = at(o0.w), v4 = at(o1.x), v5 = at(o1.y), v6 = at(o1.z),
-                     v7 = at(o1.w);
+        const int4 r = sl.rec[v];
+        if (r.x < 0) continue;
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<char*>(dst) + static_cast<unsigned long long>(static_cast<unsigned>(r.x)) * kVoxBytes);
+        const unsigned cls = static_cast<unsigned>(r.y) >> 30;
         float4 acc = vzero4();      // ATen accumulation order: x fastest, then y, then z
-        vfma(acc, v0, w0.x);
-        vfma(acc, v1, w0.y);
-        vfma(acc, v2, w0.z);
-        vfma(acc, v3, w0.w);
-        vfma(acc, v4, w1.x);
-        vfma(acc, v5, w1.y);
-        vfma(acc, v6, w1.z);
-        vfma(acc, v7, w1.w);
+        if (cls == 1u) {            // all corners inside: base + fixed strides, weights (wx wy) wz formed here
+            const float4 q = sl.wts[v];
+            const float wx0 = __int_as_float(r.z), wx1 = __int_as_float(r.w);
+            const float w00 = __fmul_rn(wx0, q.x), w10 = __fmul_rn(wx1, q.x), w01 = __fmul_rn(wx0, q.y), w11 = __fmul_rn(wx1, q.y);
+            const char* p0 = reinterpret_cast<const char*>(src) + static_cast<unsigned long long>(static_cast<unsigned>(r.y) & 0x3fffffffu) * kVoxBytes;
+            const char* p1 = p0 + sz_b;
+            auto at = [](const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
+            const float4 v0 = at(p0), v1 = at(p0 + kVoxBytes), v2 = at(p0 + sy_b), v3 = at(p0 + sy_b + kVoxBytes), v4 = at(p1),
+                         v5 = at(p1 + kVoxBytes), v6 = at(p1 + sy_b), v7 = at(p1 + sy_b + kVoxBytes);
+            vfma(acc, v0, __fmul_rn(w00, q.z));
+            vfma(acc, v1, __fmul_rn(w10, q.z));
+            vfma(acc, v2, __fmul_rn(w01, q.z));
+            vfma(acc, v3, __fmul_rn(w11, q.z));
+            vfma(acc, v4, __fmul_rn(w00, q.w));
+            vfma(acc, v5, __fmul_rn(w10, q.w));
+            vfma(acc, v6, __fmul_rn(w01, q.w));
+            vfma(acc, v7, __fmul_rn(w11, q.w));
+        } else if (cls == 2u) {     // partly outside: clamped offsets, masked weights from the full tables
+            const int4 o0 = *reinterpret_cast<const int4*>(&s.off[v][0]), o1 = *reinterpret_cast<const int4*>(&s.off[v][4]);
+            const float4 w0 = *reinterpret_cast<const float4*>(&s.w[v][0]), w1 = *reinterpret_cast<const float4*>(&s.w[v][4]);
+            auto at = [&](int off) {
+                return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(src) +
+                                                             static_cast<unsigned long long>(static_cast<unsigned>(off)) * kVoxBytes));
+            };
+            const float4 v0 = at(o0.x), v1 = at(o0.y), v2 = at(o0.z), v3 = at(o0.w), v4 = at(o1.x), v5 = at(o1.y), v6 = at(o1.z),
+                         v7 = at(o1.w);
+            vfma(acc, v0, w0.x);
+            vfma(acc, v1, w0.y);
+            vfma(acc, v2, w0.z);
+            vfma(acc, v3, w0.w);
+            vfma(acc, v4, w1.x);
+            vfma(acc, v5, w1.y);
+            vfma(acc, v6, w1.z);
+            vfma(acc, v7, w1.w);
+        }                           // cls == 0: the sample lies outside the source volume (zeros padding): nothing to read
         if (kStream) __stcs(op, acc);       // written once, never re-read by this kernel: leave L2 to the source volumes
         else *op = acc;
     }
@@ -397,7 +430,7 @@ extern "C" int forge_rotate_fwd(const float* vox_cl, const float* affine12, cons
         const char* e = getenv("FORGE_K2_LEAN");
         return e ? atoi(e) != 0 : true;
     }();
-    if (lean && C == 128 && (shape_id == 6 || shape_id == 7 || shape_id == 0) && aligned16(vox_cl) && aligned16(out_cl) &&
+    if (lean && C == 128 && (shape_id == 6 || shape_id == 7 || shape_id == 8 || shape_id == 0) && aligned16(vox_cl) && aligned16(out_cl) &&
         static_cast<long long>(D) * H * W * 32 < 2147483647LL) {
         const float4* in4 = reinterpret_cast<const float4*>(vox_cl);
         float4* out4 = reinterpret_cast<float4*>(out_cl);
@@ -412,6 +445,7 @@ extern "C" int forge_rotate_fwd(const float* vox_cl, const float* affine12, cons
     } while (0)
         if (shape_id == 6) FORGE_K2_LEAN(6);
         else if (shape_id == 7) FORGE_K2_LEAN(7);
+        else if (shape_id == 8) FORGE_K2_LEAN(8);
         else FORGE_K2_LEAN(0);
 #undef FORGE_K2_LEAN
     } else if (C % 4 == 0 && aligned16(vox_cl) && aligned16(out_cl)) {
