@@ -163,7 +163,7 @@ class FORGE(nn.Module):
             'K': camK.reshape(b * t_all, 3, 3),
         }
         features_mv, densities_mv = self.reconstruct(features_raw, camPoses_cv2, idxs)
-        view2vol = torch.arange(b, device=device).repeat_interleave(t_all).int()
+        view2vol = torch.div(torch.arange(b * t_all, device=device), t_all, rounding_mode='floor').int()    # capture-safe
         rendered_imgs, rendered_masks, origin_proj = self.render(cameras, features_mv, densities_mv,
                                                                  return_origin_proj=True, view2vol=view2vol)
         if self.config.train.use_gt_pose:

@@ -197,3 +197,30 @@ def test_forge_forward_bf16_tensor_core_configuration_tracks_fp32(setup):
     assert (mask16 - mask).abs().max().item() <= 5e-2 * max(1.0, mask.abs().max().item())
     assert (rgb16 - rgb).abs().max().item() <= 5e-2 * max(1.0, rgb.abs().max().item())
     assert (mask16 - mask).abs().mean().item() <= 5e-3
+
+
+def test_streamed_forge_matches_eager_forward():
+    """forge_b200.pipeline.StreamedForge (FORGE.forward as one CUDA graph between double-buffered staging tensors, uploads /
+    downloads on their own streams) returns what the eager call returns, batch after batch, for different batches."""
+    import warnings
+    from forge_b200.pipeline import StreamedForge
+    cfg = syn.make_config(img_size=256, n_pts_per_ray=16, use_gt_pose=True)
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = FORGE(cfg).to(DEV).eval()
+    model.encoder_3d.density_head[6].bias.data.fill_(0.15)
+    samples = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in syn.kubric_batch(1, n_views_all=7, img_size=256, seed=s).items()}
+               for s in (1, 2, 3)]
+    with torch.no_grad():
+        want = [tuple(x.clone() for x in model({k: (v.clone() if torch.is_tensor(v) else v) for k, v in smp.items()}, None, torch.device(DEV)))
+                for smp in samples]
+        sf = StreamedForge(model, samples[0], None, depth=2)
+        outs = [(torch.empty(want[0][0].shape).pin_memory(), torch.empty(want[0][1].shape).pin_memory()) for _ in samples]
+        for smp, (o_rgb, o_mask) in zip(samples, outs):
+            sf.submit(smp, o_rgb, o_mask)
+        sf.drain()
+    for (rgb, mask), (o_rgb, o_mask) in zip(want, outs):
+        assert torch.isfinite(o_rgb).all() and o_rgb.abs().max() > 0
+        assert (o_rgb - rgb.cpu()).abs().max().item() <= 1e-5
+        assert (o_mask - mask.cpu()).abs().max().item() <= 1e-5
