@@ -171,94 +171,17 @@ __global__ void sample_points_kernel(const float* __restrict__ pts, int M, int D
 }
 
 // ---- render-volume packing -------------------------------------------------------------------------
-// One CTA per group of kPackRows consecutive padded y-rows of one (volume, z): for every channel those input
-// rows are one contiguous run (kPackRows * W floats), read with 128-bit loads, transposed through shared
-// memory ([row][x][channel], x-stride 17 / row-stride = 2 mod 32 banks) and written as zero-bordered
-// channels-last rows [W+2][16] plus the density-quad rows [W+1][4].  HBM-bound: reads V*17*D*H*W*4 bytes,
-// writes ~1.1x that + 4x the density.
+// forge_pack_volume: [V][16][D][H][W] (or channels-last [V][D][H][W][16]) features + [V][D][H][W] density -> zero-bordered
+// channels-last feat_pad [V][D+2][H+2][W+2][16] and density quads [V][D+2][H+1][W+1][4].  HBM-bound: reads V*17*D*H*W*4
+// bytes, writes ~1.1x that + 4x the density.
+//
+// Round 1 / first half of round 2 went through a shared-memory transpose (one CTA per group of padded y-rows, 128-bit
+// loads, [row][x][channel] tile, load phase -> barrier -> store phase): 56.6 % of the HBM peak at cfg-2, 76 % at cfg-4
+// with 4 rows per CTA.  The kernel below needs no shared memory: one thread per padded voxel gathers its 16 channels
+// with 16 independent scalar loads (a warp reads 128 contiguous bytes per channel) and writes its 64-byte record with
+// four 16-byte stores; one thread per density quad.  No barrier, no phases, fine-grained CTAs (short tail): 67.6 % at
+// cfg-2 (0.044 -> 0.037 ms), 88.6 % at cfg-4 (0.511 -> 0.439 ms) -- profiles/r02_ab_pack_direct.jsonl.
 constexpr int kPackThreads = 256;
-
-template <int kPackRows>
-__global__ void __launch_bounds__(kPackThreads)
-pack_volume_kernel(const float* __restrict__ feat, int feat_cl, const float* __restrict__ dens,
-                   float* __restrict__ feat_pad, float4* __restrict__ dens_quad, int D, int H, int W, int ygroups) {
-    extern __shared__ __align__(16) float sm[];
-    const int Wp = W + 2, Hp = H + 2, Wq = W + 1, Hq = H + 1;
-    const int TS = W * 17 + 2;                          // floats per transposed row
-    float* tile = sm;                                   // [kPackRows][W][17]
-    float* drow = sm + kPackRows * TS;                  // [kPackRows + 1][W + 2] density rows y0-1 .. y0+kPackRows-1
-    const int v = blockIdx.y;
-    const int zp = blockIdx.x / ygroups, yp0 = (blockIdx.x - zp * ygroups) * kPackRows;
-    const int z = zp - 1;
-    const long long S = static_cast<long long>(D) * H * W;
-    const bool zin = (z >= 0 && z < D);
-    // interior rows of this group: padded rows yp0 + ry with y = yp0 + ry - 1 in [0, H)
-    const int ry_lo = max(0, 1 - yp0), ry_hi = min(kPackRows, H + 1 - yp0);       // [ry_lo, ry_hi)
-
-    if (zin && !feat_cl && ry_hi > ry_lo) {
-        const int rows = ry_hi - ry_lo;
-        const float* base = feat + static_cast<long long>(v) * 16 * S + (static_cast<long long>(z) * H + (yp0 + ry_lo - 1)) * W;
-        if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15u) == 0) {
-            const int wq = W >> 2, per_ch = rows * wq;
-            for (int u = threadIdx.x; u < 16 * per_ch; u += kPackThreads) {
-                const int ch = u / per_ch, rem = u - ch * per_ch;
-                const int ry = rem / wq, xq = rem - ry * wq;
-                const float4 val = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(ch) * S + ry * W) + xq);
-                float* t = tile + (ry_lo + ry) * TS + (4 * xq) * 17 + ch;
-                t[0] = val.x;
-                t[17] = val.y;
-                t[34] = val.z;
-                t[51] = val.w;
-            }
-        } else {
-            const int per_ch = rows * W;
-            for (int u = threadIdx.x; u < 16 * per_ch; u += kPackThreads) {
-                const int ch = u / per_ch, rem = u - ch * per_ch;
-                const int ry = rem / W, x = rem - ry * W;
-                tile[(ry_lo + ry) * TS + x * 17 + ch] = __ldg(base + static_cast<long long>(ch) * S + ry * W + x);
-            }
-        }
-    }
-    for (int e = threadIdx.x; e < (kPackRows + 1) * Wp; e += kPackThreads) {
-        const int ry = e / Wp, xs = e - ry * Wp;        // xs = x + 1
-        const int y = yp0 + ry - 1, x = xs - 1;
-        float val = 0.f;
-        if (zin && y >= 0 && y < H && x >= 0 && x < W)
-            val = __ldg(dens + static_cast<long long>(v) * S + (static_cast<long long>(z) * H + y) * W + x);
-        drow[ry * Wp + xs] = val;
-    }
-    __syncthreads();
-
-    const int nrows = min(kPackRows, Hp - yp0);
-    // feature rows: nrows x (Wp * 4) float4, contiguous in feat_pad (consecutive padded rows follow each other)
-    float4* out = reinterpret_cast<float4*>(feat_pad + ((static_cast<long long>(v) * (D + 2) + zp) * Hp + yp0) * Wp * 16);
-    const int row4 = Wp * 4;
-    for (int u = threadIdx.x; u < nrows * row4; u += kPackThreads) {
-        const int ry = u / row4, e = u - ry * row4;
-        const int xp = e >> 2, c4 = (e & 3) * 4;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (zin && ry >= ry_lo && ry < ry_hi && xp >= 1 && xp <= W) {
-            if (feat_cl) {
-                const int y = yp0 + ry - 1;
-                o = __ldg(reinterpret_cast<const float4*>(feat + (static_cast<long long>(v) * S + (static_cast<long long>(z) * H + y) * W + xp - 1) * 16 + c4));
-            } else {
-                const float* t = tile + ry * TS + (xp - 1) * 17 + c4;
-                o = make_float4(t[0], t[1], t[2], t[3]);
-            }
-        }
-        out[u] = o;
-    }
-    // density quads: row yq = yp covers y = yp - 1 (drow[ry]) and y + 1 = yp (drow[ry + 1]); rows yq <= H
-    const int qrows = min(kPackRows, Hq - yp0);
-    if (qrows > 0) {
-        float4* q = dens_quad + ((static_cast<long long>(v) * (D + 2) + zp) * Hq + yp0) * Wq;
-        for (int u = threadIdx.x; u < qrows * Wq; u += kPackThreads) {
-            const int ry = u / Wq, xq = u - ry * Wq;
-            const float* d0 = drow + ry * Wp, * d1 = d0 + Wp;
-            q[u] = make_float4(d0[xq], d0[xq + 1], d1[xq], d1[xq + 1]);
-        }
-    }
-}
 
 // gradient of the padded feature volume back to the caller's layout (interior voxels only)
 __global__ void __launch_bounds__(kPackThreads)
@@ -329,6 +252,62 @@ int forge_sample_points(const float* pts, int M, int D, int H, int W, int align_
 
 }  // extern "C"
 
+namespace forge {
+
+__global__ void __launch_bounds__(kPackThreads)
+pack_volume_kernel(const float* __restrict__ feat, int feat_cl, const float* __restrict__ dens, float4* __restrict__ feat_pad,
+                   float4* __restrict__ dens_quad, int D, int H, int W, long long n_vox, long long n_quad) {
+    const int Wp = W + 2, Hp = H + 2, Wq = W + 1, Hq = H + 1;
+    const long long S = static_cast<long long>(D) * H * W;
+    const long long i = blockIdx.x * 256LL + threadIdx.x;
+    if (i < n_vox) {
+        const int xp = static_cast<int>(i % Wp), yp = static_cast<int>((i / Wp) % Hp);
+        const long long vz = i / (static_cast<long long>(Wp) * Hp);
+        const int zp = static_cast<int>(vz % (D + 2));
+        const long long v = vz / (D + 2);
+        float c[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) c[e] = 0.f;
+        if (xp >= 1 && xp <= W && yp >= 1 && yp <= H && zp >= 1 && zp <= D) {
+            const long long vox = (static_cast<long long>(zp - 1) * H + (yp - 1)) * W + (xp - 1);
+            if (feat_cl) {          // channels-last producer: the record is already contiguous
+                const float4* p = reinterpret_cast<const float4*>(feat + (v * S + vox) * 16);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 q = __ldg(p + e);
+                    c[4 * e] = q.x, c[4 * e + 1] = q.y, c[4 * e + 2] = q.z, c[4 * e + 3] = q.w;
+                }
+            } else {
+                const float* p = feat + v * 16 * S + vox;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) c[e] = __ldg(p + e * S);
+            }
+        }
+        float4* o = feat_pad + i * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = make_float4(c[4 * e], c[4 * e + 1], c[4 * e + 2], c[4 * e + 3]);
+    }
+    if (i < n_quad) {
+        const int xq = static_cast<int>(i % Wq), yq = static_cast<int>((i / Wq) % Hq);
+        const long long vz = i / (static_cast<long long>(Wq) * Hq);
+        const int z = static_cast<int>(vz % (D + 2)) - 1;
+        const long long v = vz / (D + 2);
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (z >= 0 && z < D) {
+            const float* d = dens + v * S + static_cast<long long>(z) * H * W;
+            const int y0 = yq - 1, x0 = xq - 1;
+            const bool ya = y0 >= 0, yb = yq < H, xa = x0 >= 0, xb = xq < W;
+            if (ya && xa) q.x = __ldg(d + y0 * W + x0);
+            if (ya && xb) q.y = __ldg(d + y0 * W + xq);
+            if (yb && xa) q.z = __ldg(d + yq * W + x0);
+            if (yb && xb) q.w = __ldg(d + yq * W + xq);
+        }
+        dens_quad[i] = q;
+    }
+}
+
+}  // namespace forge
+
 extern "C" int forge_pack_volume(const float* feat, int feat_channels_last, const float* dens, float* feat_pad,
                                  float* dens_quad, int V, int D, int H, int W, void* stream) {
     FORGE_RANGE("forge_pack_volume");
@@ -339,28 +318,11 @@ extern "C" int forge_pack_volume(const float* feat, int feat_channels_last, cons
     if (V > 65535) return fail(fn, "more than 65535 volumes in one launch");
     if (!aligned16(dens_quad)) return fail(fn, "dens_quad must be 16-byte aligned");
     if (!aligned16(feat_pad) || (feat_channels_last && !aligned16(feat))) return fail(fn, "feat_pad / feat must be 16-byte aligned");
-    static const int rows_env = [] {        // tuning knob (development): padded y-rows per CTA
-        const char* e = getenv("FORGE_PACK_ROWS");
-        return e ? atoi(e) : 0;
-    }();
-    // ~37 KB of shared memory per CTA (6 CTAs per SM) is the sweet spot: 8 rows up to W = 64, 4 rows beyond (measured on B200:
-    // cfg-2 W = 64: 4 / 8 / 16 rows = 0.046 / 0.044 / 0.058 ms; cfg-4 W = 128: 0.511 / 0.683 / 1.554 ms = 76 / 57 / 25 % of the HBM peak)
-    const int rows = (rows_env == 4 || rows_env == 8 || rows_env == 16) ? rows_env : (W > 64 ? 4 : 8);
-    const size_t smem = sizeof(float) * (rows * (W * 17 + 2) + (rows + 1) * (W + 2));
-    if (smem > 200 * 1024) return fail(fn, "volume rows longer than 360 voxels are not supported");
-    const int ygroups = (H + 2 + rows - 1) / rows;
-    dim3 grid((D + 2) * ygroups, V);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float4* dq = reinterpret_cast<float4*>(dens_quad);
-#define FORGE_PACK(R)                                                                                                  \
-    do {                                                                                                               \
-        if (int rc = ensure_dynamic_smem(fn, reinterpret_cast<const void*>(pack_volume_kernel<R>), smem)) return rc;   \
-        pack_volume_kernel<R><<<grid, kPackThreads, smem, st>>>(feat, feat_channels_last, dens, feat_pad, dq, D, H, W, ygroups); \
-    } while (0)
-    if (rows == 4) FORGE_PACK(4);
-    else if (rows == 16) FORGE_PACK(16);
-    else FORGE_PACK(8);
-#undef FORGE_PACK
+    const long long n_vox = static_cast<long long>(V) * (D + 2) * (H + 2) * (W + 2);
+    const long long n_quad = static_cast<long long>(V) * (D + 2) * (H + 1) * (W + 1);
+    if ((n_vox + kPackThreads - 1) / kPackThreads > 2147483647LL) return fail(fn, "volume batch too large for one launch");
+    pack_volume_kernel<<<static_cast<unsigned>((n_vox + kPackThreads - 1) / kPackThreads), kPackThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        feat, feat_channels_last, dens, reinterpret_cast<float4*>(feat_pad), reinterpret_cast<float4*>(dens_quad), D, H, W, n_vox, n_quad);
     return check_launch(fn);
 }
 
