@@ -386,103 +386,6 @@ rotate_bwd_kernel(const VecT* __restrict__ in, const float* __restrict__ affine,
     }
 }
 
-// ---- backward to the volumes as a GATHER over source voxels (round 2) -----------------------------------------------------
-// rotate_bwd_kernel scatters 8 x C floats per OUTPUT voxel with vector REDs; REDs cost ~1.2 cycles per active lane in the
-// LSU, which bounds that kernel (8 RED.128 warp-instructions per voxel of 128 channels).  Here a warp owns one SOURCE voxel
-// X: the output voxels whose trilinear footprint contains X are the integer points of a small parallelepiped (the sample
-// position is affine in the output index: p = B o + c, so the candidates are the lattice points of B^-1 ([X - 1, X + 1)^3),
-// at most 4 x 4 x 4 for a rotation); the lanes test the candidates in parallel with EXACTLY the forward's arithmetic
-// (rotate_tri), the hits are ballot-ed, and every lane (one float4 of channels) accumulates weight x g_out over the hits in
-// registers: one coalesced 512-byte read per hit, one RED per lane and source voxel at the end (8x fewer than the scatter;
-// plain accumulation would need jobs with distinct sources, which the ABI does not promise).
-constexpr int kGatherWarps = 8;
-constexpr int kGatherMaxK = 4;          // float4 chunks per lane: C <= 512
-
-__global__ void __launch_bounds__(32 * kGatherWarps)
-rotate_bwd_gather_kernel(const float* __restrict__ affine, const int* __restrict__ jobs, const float* __restrict__ gx,
-                         const float* __restrict__ gy, const float* __restrict__ gz, float inv_max,
-                         const float4* __restrict__ g_out, float4* __restrict__ grad_in, int CU, int D, int H, int W) {
-    __shared__ float sA[12], sBi[9], sc[3], shw[3];
-    const int m = blockIdx.y;
-    const RotJob job = {jobs[3 * m], jobs[3 * m + 1], jobs[3 * m + 2]};
-    const long long vol = static_cast<long long>(D) * H * W;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float4* go = g_out + static_cast<long long>(job.dst) * vol * CU;
-    float4* gin = grad_in + static_cast<long long>(job.src) * vol * CU;
-    const long long xlin = static_cast<long long>(blockIdx.x) * kGatherWarps + warp;
-
-    if (job.kind == 1) {   // view-0 passthrough: the gradient passes through unchanged
-        if (xlin < vol)
-            for (int cu = lane; cu < CU; cu += 32) vred(gin + xlin * CU + cu, go[xlin * CU + cu]);
-        return;
-    }
-    if (threadIdx.x < 12) sA[threadIdx.x] = affine[12 * m + threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // p_i = ((A_i . [g(o), 1]) inv_max + 1) size_i / 2 - 1/2 with g_j(o_j) ~ g_j[0] + o_j dg_j  =>  p = B o + c
-        const float g0[3] = {gx[0], gy[0], gz[0]};
-        const float dg[3] = {W > 1 ? gx[1] - gx[0] : 0.f, H > 1 ? gy[1] - gy[0] : 0.f, D > 1 ? gz[1] - gz[0] : 0.f};
-        const float half[3] = {0.5f * W, 0.5f * H, 0.5f * D};
-        float B[9];
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j) B[3 * i + j] = sA[4 * i + j] * dg[j] * inv_max * half[i];
-            sc[i] = ((sA[4 * i] * g0[0] + sA[4 * i + 1] * g0[1] + sA[4 * i + 2] * g0[2] + sA[4 * i + 3]) * inv_max + 1.f) * half[i] - 0.5f;
-        }
-        const float det = B[0] * (B[4] * B[8] - B[5] * B[7]) - B[1] * (B[3] * B[8] - B[5] * B[6]) + B[2] * (B[3] * B[7] - B[4] * B[6]);
-        const float id = 1.f / det;             // a singular affine gives inf / nan half-widths: every output voxel becomes a candidate
-        sBi[0] = (B[4] * B[8] - B[5] * B[7]) * id, sBi[1] = (B[2] * B[7] - B[1] * B[8]) * id, sBi[2] = (B[1] * B[5] - B[2] * B[4]) * id;
-        sBi[3] = (B[5] * B[6] - B[3] * B[8]) * id, sBi[4] = (B[0] * B[8] - B[2] * B[6]) * id, sBi[5] = (B[2] * B[3] - B[0] * B[5]) * id;
-        sBi[6] = (B[3] * B[7] - B[4] * B[6]) * id, sBi[7] = (B[1] * B[6] - B[0] * B[7]) * id, sBi[8] = (B[0] * B[4] - B[1] * B[3]) * id;
-        for (int i = 0; i < 3; ++i) shw[i] = fabsf(sBi[3 * i]) + fabsf(sBi[3 * i + 1]) + fabsf(sBi[3 * i + 2]);
-    }
-    __syncthreads();
-    if (xlin >= vol) return;
-    const int x = static_cast<int>(xlin % W), y = static_cast<int>((xlin / W) % H), z = static_cast<int>(xlin / (static_cast<long long>(W) * H));
-    // candidate box: B^-1 maps the cube [X - 1, X + 1]^3 (centre X) into a box of half-widths sum_j |B^-1_ij| (+ slack for the
-    // rounding of the linearised tables; extra candidates are rejected by the exact test below)
-    const float rx = static_cast<float>(x) - sc[0], ry = static_cast<float>(y) - sc[1], rz = static_cast<float>(z) - sc[2];
-    const int size[3] = {W, H, D};
-    int lo[3], n[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float oc = sBi[3 * i] * rx + sBi[3 * i + 1] * ry + sBi[3 * i + 2] * rz;
-        const float hw = shw[i] * 1.001f + 0.05f;
-        float a = ceilf(oc - hw), b = floorf(oc + hw);
-        if (!(a >= 0.f)) a = 0.f;                                  // also catches nan
-        if (a > static_cast<float>(size[i])) a = static_cast<float>(size[i]);
-        if (!(b <= static_cast<float>(size[i] - 1))) b = static_cast<float>(size[i] - 1);
-        lo[i] = static_cast<int>(a);
-        n[i] = max(static_cast<int>(b) - lo[i] + 1, 0);
-    }
-    const int total = n[0] * n[1] * n[2];
-    float4 acc[kGatherMaxK];
-#pragma unroll
-    for (int k = 0; k < kGatherMaxK; ++k) acc[k] = vzero4();
-    for (int base = 0; base < total; base += 32) {
-        const int cand = base + lane;
-        float wgt = 0.f;
-        int oidx = 0;
-        if (cand < total) {
-            const int w = lo[0] + cand % n[0], h = lo[1] + (cand / n[0]) % n[1], d = lo[2] + cand / (n[0] * n[1]);
-            const Tri t = rotate_tri(sA, gx[w], gy[h], gz[d], inv_max, D, H, W);
-            const unsigned dx = static_cast<unsigned>(x - t.x0), dy = static_cast<unsigned>(y - t.y0), dz = static_cast<unsigned>(z - t.z0);
-            if (dx <= 1u && dy <= 1u && dz <= 1u) wgt = tri_weight(t, static_cast<int>(dx | (dy << 1) | (dz << 2)));
-            oidx = (d * H + h) * W + w;
-        }
-        for (unsigned hits = __ballot_sync(0xffffffffu, wgt != 0.f); hits; hits &= hits - 1) {
-            const int src_lane = __ffs(hits) - 1;
-            const float wv = __shfl_sync(0xffffffffu, wgt, src_lane);
-            const long long o = static_cast<long long>(__shfl_sync(0xffffffffu, oidx, src_lane)) * CU;
-#pragma unroll
-            for (int k = 0; k < kGatherMaxK; ++k)
-                if (lane + 32 * k < CU) vfma(acc[k], __ldg(go + o + lane + 32 * k), wv);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kGatherMaxK; ++k)
-        if (lane + 32 * k < CU) vred(gin + xlin * CU + lane + 32 * k, acc[k]);
-}
-
 static int rotate_check(const char* fn, const void* vox, const void* aff, const void* jobs, const void* gx,
                         const void* gy, const void* gz, float gmax, int M, int C, int D, int H, int W) {
     if (!vox || !aff || !jobs || !gx || !gy || !gz) return fail(fn, "null pointer");
@@ -601,23 +504,7 @@ extern "C" int forge_rotate_bwd(const float* vox_cl, const float* affine12, cons
     dim3 grid(tiles_x * tiles_y * tiles_z, M);
     const float inv_max = 1.0f / grid_coord_max;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static const bool gather = [] {          // tuning knob (development): 0 = the round-1 scatter for grad_vox
-        const char* e = getenv("FORGE_K2B_GATHER");
-        return e ? atoi(e) != 0 : true;
-    }();
-    const long long vol = static_cast<long long>(D) * H * W;
-    if (gather && grad_vox_cl && C % 4 == 0 && C / 4 <= 32 * kGatherMaxK && aligned16(vox_cl) && aligned16(g_out_cl) &&
-        aligned16(grad_vox_cl) && vol < 2147483647LL) {
-        // grad_vox by the gather kernel; grad_affine12 (needs the corner values per output voxel) by the tile kernel without its scatter
-        dim3 ggrid(static_cast<unsigned>((vol + kGatherWarps - 1) / kGatherWarps), M);
-        rotate_bwd_gather_kernel<<<ggrid, 32 * kGatherWarps, 0, st>>>(affine12, jobs, gx, gy, gz, inv_max,
-                                                                     reinterpret_cast<const float4*>(g_out_cl),
-                                                                     reinterpret_cast<float4*>(grad_vox_cl), C / 4, D, H, W);
-        if (grad_affine12)
-            rotate_bwd_kernel<float4><<<grid, kRotThreads, 0, st>>>(
-                reinterpret_cast<const float4*>(vox_cl), affine12, jobs, gx, gy, gz, inv_max,
-                reinterpret_cast<const float4*>(g_out_cl), nullptr, grad_affine12, C / 4, D, H, W, tiles_x, tiles_y);
-    } else if (C % 4 == 0 && aligned16(vox_cl) && aligned16(g_out_cl) && (!grad_vox_cl || aligned16(grad_vox_cl))) {
+    if (C % 4 == 0 && aligned16(vox_cl) && aligned16(g_out_cl) && (!grad_vox_cl || aligned16(grad_vox_cl))) {
         rotate_bwd_kernel<float4><<<grid, kRotThreads, 0, st>>>(
             reinterpret_cast<const float4*>(vox_cl), affine12, jobs, gx, gy, gz, inv_max,
             reinterpret_cast<const float4*>(g_out_cl), reinterpret_cast<float4*>(grad_vox_cl), grad_affine12, C / 4, D, H,
