@@ -29,6 +29,33 @@ def test_library_exports_every_declared_symbol():
     assert lib.forge_abi_version() == _lib.ABI_VERSION
 
 
+def test_ctypes_signatures_match_header_prototypes():
+    """Every prototype of include/forge_b200.h against forge_b200/_lib.py's ctypes table: same number of parameters and the same
+    kind per parameter (pointer / int / long long / float / unsigned) -- an ABI change that forgets one side fails here, on CPU."""
+    from forge_b200 import _lib
+    with open(os.path.join(ROOT, "include", "forge_b200.h")) as fh:
+        text = re.sub(r"/\*.*?\*/", "", fh.read(), flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = re.findall(r"\b([A-Za-z_][A-Za-z0-9_ ]*?[ \*])\s*(forge_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text)
+    assert len(protos) == len(_lib._SIGNATURES)
+
+    def kind(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            return "ptr"
+        base = " ".join(decl.split()[:-1]) if len(decl.split()) > 1 else decl      # drop the parameter name
+        return {"int": "int", "long long": "ll", "float": "float", "unsigned": "uint", "unsigned int": "uint"}[base.replace("const ", "")]
+
+    ckind = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "int", ctypes.c_longlong: "ll", ctypes.c_float: "float",
+             ctypes.c_uint: "uint"}
+    for ret, name, params in protos:
+        restype, argtypes = _lib._SIGNATURES[name]
+        params = params.strip()
+        want = [] if params in ("", "void") else [kind(p) for p in params.split(",")]
+        assert [ckind[a] for a in argtypes] == want, name
+        assert ckind[restype] == ("ptr" if "*" in ret else kind(ret.strip() + " x")), name
+
+
 def test_error_reporting_without_gpu():
     from forge_b200 import _lib
     with pytest.raises(RuntimeError, match="forge_raymarch_fwd: null pointer"):
