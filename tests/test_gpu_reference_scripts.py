@@ -1,4 +1,4 @@
-"""The reference's OWN demo.py, unmodified, executed end to end against forge_b200 through compat/ (BASELINE.json north_star:
+"""The reference's OWN demo.py and kubric_train_pose_3D.py, unmodified, executed end to end against forge_b200 through compat/ (BASELINE.json north_star:
 "kubric_train_*.py and demo.py run unchanged").  Needs the staged reference tarball (tools/stage_reference.sh ->
 baseline/_ref/forge_reference.tar.gz, git-ignored) or a checkout at $FORGE_REFERENCE; skipped otherwise.  The script predicts
 poses, runs its 3 x 2001 refinement iterations through rotate -> fuse -> heads -> render -> backward, renders 28 novel views
@@ -26,6 +26,22 @@ def test_reference_demo_py_runs_unchanged():
     summary = json.loads(last[-1])
     assert summary["rc"] == 0
     assert summary["gifs"] == ["0_0.gif", "1_0.gif", "2_0.gif"]          # one 360-degree render per demo case
+
+
+@pytest.mark.skipif(not HAVE, reason="no reference checkout / staged tarball")
+def test_reference_kubric_train_pose_3d_runs_unchanged():
+    """The reference's kubric_train_pose_3D.py (training step 1.1: config/kubric/gt_pose.yaml, FORGE_poseEstimator3D with every
+    parameter trainable, VGG perceptual loss, SyncBatchNorm + DDP) launched with torchrun on one GPU, unmodified apart from the
+    run length of its yaml: 2 x 4 iterations through lift -> rotate -> ConvGRU -> heads -> render (30 views per object) ->
+    backward (K1 / K2 gradients to the volumes) -> Adam, loss printed finite every iteration."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_reference_script.py"), "train_pose3d", "--gpus", "1",
+                          "--iters", "4", "--batch", "4"], capture_output=True, text=True, timeout=900)
+    last = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    summary = json.loads(last[-1])
+    assert summary["rc"] == 0
+    losses = [float(l.split("recon_img_mv: ")[1].split(" ")[0]) for l in summary["log_lines"] if "recon_img_mv" in l]
+    assert len(losses) >= 4 and all(0.0 < x < 10.0 for x in losses)
 
 
 JOINT = r'''

@@ -3,6 +3,8 @@
 
     python tools/run_reference_script.py demo                 # demo.py --cfg config/demo/demo.yaml
     python tools/run_reference_script.py train --gpus 2       # kubric_train_joint.py (step 3.3 yaml, SyncBN + DDP), a few iterations
+    python tools/run_reference_script.py train_pose3d --gpus 2   # kubric_train_pose_3D.py (step 1.1 gt_pose.yaml: FORGE_poseEstimator3D,
+                                                                 # every parameter trainable: K1 / K2 backward to the volumes)
 
 The reference checkout comes from $FORGE_REFERENCE, /root/reference, or the staged tarball baseline/_ref/forge_reference.tar.gz
 (tools/stage_reference.sh); it is copied / extracted into a scratch directory because the scripts write ./output and ./log next
@@ -74,9 +76,30 @@ print("checkpoints written")
 '''
 
 
+MAKE_CKPT_POSE3D = r'''
+import os, sys, torch, warnings
+warnings.simplefilter("ignore")
+from config.config import config, update_config
+update_config(sys.argv[1])
+from models.model_single_pose_estimator import FORGE_poseEstimator3D
+torch.manual_seed(0)
+m = FORGE_poseEstimator3D(config)
+m.encoder_3d.density_head[6].bias.data.fill_(0.1)      # random-init heads end in ReLU: keep the density volume non-empty
+opt = torch.optim.Adam(m.parameters(), lr=config.train.lr)
+os.makedirs(sys.argv[2], exist_ok=True)
+torch.save({'epoch': 1, 'state_dict': m.state_dict(), 'optimizer': opt.state_dict()}, os.path.join(sys.argv[2], 'cpt_last.pth.tar'))
+print("checkpoint written")
+'''
+
+TRAIN_MODES = {      # what -> (script, yaml under config/kubric, checkpoint maker)
+    "train": ("kubric_train_joint.py", "joint_pose_2d3d", None),
+    "train_pose3d": ("kubric_train_pose_3D.py", "gt_pose", MAKE_CKPT_POSE3D),
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["demo", "train"])
+    ap.add_argument("what", choices=["demo", "train", "train_pose3d"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--iters", type=int, default=6, help="train: iterations per rank")
     ap.add_argument("--batch", type=int, default=4, help="train: objects per rank (reference: 4)")
@@ -98,8 +121,9 @@ def main():
             sys.stdout.write(res.stdout[-3000:])
             sys.stderr.write(res.stderr[-3000:])
         else:
-            # the step-3.3 yaml with a short run: resume from a synthetic epoch-1 checkpoint, stop after args.iters iterations
-            src_yaml = os.path.join(ref, "config", "kubric", "joint_pose_2d3d.yaml")
+            # the reference's yaml with a short run: resume from a synthetic epoch-1 checkpoint, stop after args.iters iterations
+            script, yaml_name, ckpt_maker = TRAIN_MODES[args.what]
+            src_yaml = os.path.join(ref, "config", "kubric", yaml_name + ".yaml")
             yaml_txt = open(src_yaml).read()
             import re
             yaml_txt = re.sub(r"total_iteration:\s*\d+", "total_iteration: %d" % (2 * args.iters), yaml_txt)
@@ -108,16 +132,16 @@ def main():
             yaml_txt = re.sub(r"print_freq:\s*\d+", "print_freq: 1", yaml_txt)
             yaml_txt = re.sub(r"vis_freq:\s*\d+", "vis_freq: 1000000", yaml_txt)
             yaml_txt = re.sub(r"workers:\s*\d+", "workers: 2", yaml_txt)
-            cfg = os.path.join(ref, "config", "kubric", "joint_pose_2d3d_short.yaml")
+            cfg = os.path.join(ref, "config", "kubric", yaml_name + "_short.yaml")
             open(cfg, "w").write(yaml_txt)
             exp = re.search(r"exp_name:\s*'?([\w-]+)'?", yaml_txt).group(1)
-            out_dir = os.path.join(ref, "output", "kubric", "joint_pose_2d3d_short", exp)
-            subprocess.run([sys.executable, "-c", MAKE_CKPT, cfg, out_dir], cwd=ref, env=env, check=True)
+            out_dir = os.path.join(ref, "output", "kubric", yaml_name + "_short", exp)
+            subprocess.run([sys.executable, "-c", ckpt_maker or MAKE_CKPT, cfg, out_dir], cwd=ref, env=env, check=True)
             env["FORGE_SYNTHETIC_SEQS"] = str(args.gpus * args.batch * args.iters)       # len(train_loader) = iters per rank
             launch = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                       "--master-addr", "127.0.0.1", "--master-port", "29533", "--no-python", "bash", "-c",
                       # torchrun passes --local-rank; the reference parses --local_rank
-                      "exec %s kubric_train_joint.py --cfg %s --local_rank $LOCAL_RANK" % (sys.executable, cfg)]
+                      "exec %s %s --cfg %s --local_rank $LOCAL_RANK" % (sys.executable, script, cfg)]
             t0 = time.time()
             res = subprocess.run(launch, cwd=ref, env=env, capture_output=True, text=True)
             summary.update(rc=res.returncode, seconds=round(time.time() - t0, 1))
