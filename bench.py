@@ -611,6 +611,32 @@ def e2e_model_leg(dev, args):
         h_mask.copy_(mask, non_blocking=True)
     res = {}
     steps = 20
+
+    def streamed(tag):
+        """the same forward replayed as one CUDA graph with the next batch's uploads and the previous batch's downloads on their own
+        streams (forge_b200.pipeline.StreamedForge), in the model's current configuration"""
+        from forge_b200.pipeline import StreamedForge
+        outs = [(torch.empty_like(h_rgb).pin_memory(), torch.empty_like(h_mask).pin_memory()) for _ in range(2)]
+        with torch.no_grad():
+            sf = StreamedForge(model, sample, None, depth=2, device=dev)
+            for i in range(4):
+                sf.submit(sample, *outs[i % 2])
+            sf.drain()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                sf.submit(sample, *outs[i % 2])
+            sf.drain()
+            e1.record()
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        res[tag] = {"ms_per_step": ms, "rays_per_s": b * t_all * (CFG['img_size'] // 2) ** 2 / (ms * 1e-3),
+                    "views_per_s": b * t_all / (ms * 1e-3), "h2d_bytes_per_step": sf.h2d_bytes, "d2h_bytes_per_step": sf.d2h_bytes,
+                    "api": "forge_b200.pipeline.StreamedForge.submit(sample, out_rgb, out_mask): pinned host batch -> H2D (5 input "
+                           "views + cameras) -> FORGE.forward as one CUDA graph -> D2H, 2 batches in flight"}
+        del sf
+
     for name, prep in (("fp32", lambda: None),
                        ("bf16_lift_fusion_heads_tc_decoder", lambda: (model.encoder_3d.channels_last_3d_(),
                                                                       setattr(model.encoder_3d, 'compute_dtype', torch.bfloat16),
@@ -629,30 +655,12 @@ def e2e_model_leg(dev, args):
         ms = e0.elapsed_time(e1) / steps
         res[name] = {"ms_per_step": ms, "rays_per_s": b * t_all * (CFG['img_size'] // 2) ** 2 / (ms * 1e-3),
                      "views_per_s": b * t_all / (ms * 1e-3)}
-    # the same forward replayed as one CUDA graph with the next batch's uploads and the previous batch's downloads on their own
-    # streams (forge_b200.pipeline.StreamedForge); bf16 configuration (the last one prepared above)
-    from forge_b200.pipeline import StreamedForge
-    outs = [(torch.empty_like(h_rgb).pin_memory(), torch.empty_like(h_mask).pin_memory()) for _ in range(2)]
-    with torch.no_grad():
-        sf = StreamedForge(model, sample, None, depth=2, device=dev)
-        for i in range(4):
-            sf.submit(sample, *outs[i % 2])
-        sf.drain()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            sf.submit(sample, *outs[i % 2])
-        sf.drain()
-        e1.record()
-        torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / steps
-    res["bf16_graphed_streamed"] = {"ms_per_step": ms, "rays_per_s": b * t_all * (CFG['img_size'] // 2) ** 2 / (ms * 1e-3),
-                                    "views_per_s": b * t_all / (ms * 1e-3), "h2d_bytes_per_step": sf.h2d_bytes,
-                                    "d2h_bytes_per_step": sf.d2h_bytes,
-                                    "api": "forge_b200.pipeline.StreamedForge.submit(sample, out_rgb, out_mask): pinned host batch -> "
-                                           "H2D (5 input views + cameras) -> FORGE.forward as one CUDA graph -> D2H, 2 batches in flight"}
-    del sf
+        tag = "fp32_graphed_streamed" if name == "fp32" else "bf16_graphed_streamed"
+        try:
+            streamed(tag)
+        except Exception as e:        # noqa: BLE001 -- a secondary number never takes the leg down
+            res[tag] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            torch.cuda.synchronize(dev)
     res.update({"api": "forge_b200.models.model.FORGE.forward(sample, dataset, device), eval mode, ground-truth poses, random-init "
                        "weights, %d objects x 5 input views -> %d rendered views at 256^2" % (b, b * t_all),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps})

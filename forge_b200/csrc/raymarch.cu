@@ -148,8 +148,8 @@ constexpr int kRaysPerCta = kBwThreads / 2;
 // kMerge: rays of a warp whose samples share the base voxel (0.5-voxel ray spacing: 16 rays of a 4x4 patch fall into ~6.7 distinct
 // base voxels) are summed by one leader pair before the RED: REDs cost ~1.2 cycles per active lane in the LSU whatever their
 // width, and that issue rate -- not L2 -- bounded the unmerged kernel (20 RED warp-instructions x 32 lanes per 16 ray-samples).
-template <bool kMerge>
-__global__ void __launch_bounds__(kBwThreads, 4)
+template <bool kMerge, int kMinBlocks>
+__global__ void __launch_bounds__(kBwThreads, kMinBlocks)
 raymarch_bwd_kernel(const float* __restrict__ feat_pad, const float4* __restrict__ dens_quad,
                     const int* __restrict__ view2vol, const float* __restrict__ cam12, const float* __restrict__ zs_g,
                     const float* __restrict__ g_feat, const float* __restrict__ g_sil,
@@ -582,14 +582,28 @@ extern "C" int forge_raymarch_bwd(const float* feat_pad, const float* dens_quad,
         if (cudaMemsetAsync(quad, 0, static_cast<size_t>(bwd_quad_bytes(V, D, H, W)), st) != cudaSuccess) return check_launch(fn);
     }
     const float4* dq = reinterpret_cast<const float4*>(dens_quad);
-    if ((merge & 1) && grad_feat_pad)
-        raymarch_bwd_kernel<true><<<grid, kBwThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, g_feat, g_sil, g_depth, grad_feat_pad,
-                                                               grad_dens_pad, grad_cam12, workspace, quad, D, H, W, S_h, S_w, P, tiles_x,
-                                                               interleave_views(V, D, H, W));
-    else
-        raymarch_bwd_kernel<false><<<grid, kBwThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, g_feat, g_sil, g_depth, grad_feat_pad,
-                                                                grad_dens_pad, grad_cam12, workspace, quad, D, H, W, S_h, S_w, P, tiles_x,
-                                                                interleave_views(V, D, H, W));
+    static const int occ_env = [] {         // tuning knob (development): resident CTAs per SM the kernel is compiled for
+        const char* e = getenv("FORGE_K1B_OCC");
+        return e ? atoi(e) : 0;
+    }();
+#define FORGE_K1B(MERGE, OCC)                                                                                                      \
+    raymarch_bwd_kernel<MERGE, OCC><<<grid, kBwThreads, 0, st>>>(feat_pad, dq, view2vol, cam12, zs, g_feat, g_sil, g_depth, grad_feat_pad, \
+                                                                 grad_dens_pad, grad_cam12, workspace, quad, D, H, W, S_h, S_w, P, tiles_x, \
+                                                                 interleave_views(V, D, H, W))
+    // measured on B200 (cfg-2, 4 / 5 / 6 CTAs per SM = 128 / 96 / 80 registers): all gradients 1.181 / 1.128 / 1.207 ms (the merged
+    // kernel spills at 80), pose only 0.688 / 0.678 / 0.661 ms
+    if ((merge & 1) && grad_feat_pad) {
+        const int occ = occ_env ? occ_env : 5;
+        if (occ == 4) FORGE_K1B(true, 4);
+        else if (occ == 6) FORGE_K1B(true, 6);
+        else FORGE_K1B(true, 5);
+    } else {
+        const int occ = occ_env ? occ_env : 6;
+        if (occ == 4) FORGE_K1B(false, 4);
+        else if (occ == 5) FORGE_K1B(false, 5);
+        else FORGE_K1B(false, 6);
+    }
+#undef FORGE_K1B
     if (quad) {
         const long long planes = static_cast<long long>(V) * (D + 2), total = planes * (H + 2) * (W + 2);
         const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
