@@ -453,6 +453,16 @@ def run_forge(args, rank, world, local_rank):
                      "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                      "algorithmic_bytes": algorithmic_bytes_k1(), "kernel_ms": k1_avg_s * 1e3,
                      "executed_samples": n_exec, "executed_fraction": n_exec / float(rays * P),
+                     # the unit that actually carries K1's operands: every executed sample reads its 8 corners x 64 B from the
+                     # shared-memory bricks; the data pipe of an SM moves 128 B per clock
+                     "shared_memory": (lambda sm_bytes, sm_peak: {
+                         "algorithmic_bytes": sm_bytes, "achieved": sm_bytes / k1_avg_s / 1e9, "peak": sm_peak, "unit": "GB/s",
+                         "frac": sm_bytes / k1_avg_s / 1e9 / sm_peak,
+                         "note": "executed samples x 8 corners x 64 B of LDS.128 traffic against SMs x 128 B/clk x the SM clock sampled "
+                                 "during the run (nominal 1965 MHz when no sample is available); secondary figure, the contract's "
+                                 "roofline above stays the HBM one"})(
+                         n_exec * 512, torch.cuda.get_device_properties(dev).multi_processor_count * 128 *
+                         ((clocks.get("sm_mhz") or 1965.0) * 1e6) / 1e9),
                      "fp32_tflops": n_exec * FLOPS_PER_SAMPLE / k1_avg_s / 1e12,
                      "fp32_tflops_note": "366 FLOP per EXECUTED sample (samples outside the volume are skipped exactly and not counted)",
                      "note": "K1 (TMA-staged bricks in shared memory, conflict-free LDS.128 corner reads) is bound by shared-memory "
