@@ -42,7 +42,14 @@ class _Slot:
 
 
 class StreamedRenderer:
-    def __init__(self, volrender, n_volumes, n_views, vol, depth=3, device=None):
+    def __init__(self, volrender, n_volumes, n_views, vol, depth=3, device=None, duplex=True):
+        """duplex=True: downloads run on their own stream, concurrently with the next batch's upload (one GPU on its own PCIe
+        link: both directions at full rate).  duplex=False: one copy stream carries both directions, the download of batch i
+        queued behind the upload of batch i + 1 -- for boxes whose host link does not sustain both directions at once (8 GPUs
+        behind one NUMA node: 23.7 GB/s per GPU one way, 13.7 GB/s each way when both run).  Kernels overlap the
+        copies either way.  ``calibrate`` measures both on the spot and keeps the faster."""
+        self.duplex = bool(duplex)
+        self.pending = None                      # duplex=False: (slot, host outputs) whose download is still to be queued
         self.m = volrender
         self.dev = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.V, self.N, self.D = n_volumes, n_views, vol
@@ -58,7 +65,8 @@ class StreamedRenderer:
     def submit(self, feat, dens, R, T, K, view2vol, out_feat, out_sil, out_depth):
         """All arguments are pinned host tensors; K is the full-resolution intrinsics (halved on the
         device copy, like VolRender.forward does to its argument).  Returns the event that fires when
-        the outputs have landed in the host tensors."""
+        the outputs have landed in the host tensors (duplex=False: the event is recorded by the NEXT submit() or by drain(),
+        which is when the download is queued -- wait on it only after one of those)."""
         s = self.slots[self.next]
         self.next = (self.next + 1) % len(self.slots)
         if s.busy:
@@ -83,15 +91,49 @@ class StreamedRenderer:
                       self.N, self.V, self.D, self.D, self.D, self.S, self.S, self.zs.numel(), st)
             self.launches += 3
             s.computed.record(self.s_cmp)
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(s.computed)
-            out_feat.copy_(s.out, non_blocking=True)
-            out_sil.copy_(s.sil, non_blocking=True)
-            out_depth.copy_(s.depth, non_blocking=True)
-            s.copied_out.record(self.s_out)
+        if self.duplex:
+            self._download(s, (out_feat, out_sil, out_depth), self.s_out)
+        else:
+            # half duplex: this batch's download goes on the upload stream AFTER the next batch's upload (or at drain), so the
+            # copies never run in both directions at once and the upload of batch i + 1 still overlaps the kernels of batch i
+            prev, self.pending = self.pending, (s, (out_feat, out_sil, out_depth))
+            if prev is not None:
+                self._download(prev[0], prev[1], self.s_in)
         return s.copied_out
 
+    def _download(self, s, outs, stream):
+        with torch.cuda.stream(stream):
+            stream.wait_event(s.computed)
+            outs[0].copy_(s.out, non_blocking=True)
+            outs[1].copy_(s.sil, non_blocking=True)
+            outs[2].copy_(s.depth, non_blocking=True)
+            s.copied_out.record(stream)
+
+    def calibrate(self, feat, dens, R, T, K, view2vol, out_feat, out_sil, out_depth, steps=24):
+        """Run ``steps`` batches in each copy mode and keep the faster one (host links differ: see __init__).  -> dict of ms."""
+        ms = {}
+        for mode in (True, False):
+            self.drain()
+            self.duplex = mode
+            for _ in range(3):
+                self.submit(feat, dens, R, T, K, view2vol, out_feat, out_sil, out_depth)
+            self.drain()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(self.dev)
+            e0.record(self.s_in)
+            for _ in range(steps):
+                self.submit(feat, dens, R, T, K, view2vol, out_feat, out_sil, out_depth)
+            self.drain()
+            e1.record(self.s_in)
+            e1.synchronize()
+            ms["duplex" if mode else "half_duplex"] = e0.elapsed_time(e1) / steps
+        self.duplex = ms["duplex"] <= ms["half_duplex"]
+        return ms
+
     def drain(self):
+        if self.pending is not None:
+            self._download(self.pending[0], self.pending[1], self.s_in)
+            self.pending = None
         for s in self.slots:
             if s.busy:
                 s.copied_out.synchronize()

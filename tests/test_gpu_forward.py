@@ -259,13 +259,21 @@ def test_cpu_inputs_fail_loudly():
         Rotate_world(syn.make_config())(torch.zeros(1, 2, 4, 8, 8, 8), torch.eye(4).repeat(1, 2, 1, 1), grid_size=8)
 
 
-def test_streamed_renderer_matches_direct_call():
-    """Host-to-host pipeline (3 streams, batches in flight) returns exactly what the direct call returns."""
+@pytest.mark.parametrize("duplex", [True, False])
+def test_streamed_renderer_matches_direct_call(duplex):
+    """Host-to-host pipeline (batches in flight; downloads on their own stream, or queued behind the next upload on the copy
+    stream) returns exactly what the direct call returns; calibrate() leaves a working pipeline behind."""
     from forge_b200.pipeline import StreamedRenderer
     cfg = syn.make_config(img_size=64, n_pts_per_ray=24)
     m = VolRender(cfg).to(DEV).eval()
     batches = [syn.render_inputs(2, 3, 64, 16, seed=s) for s in range(5)]
-    sr = StreamedRenderer(m, 2, 6, 16, depth=2)
+    sr = StreamedRenderer(m, 2, 6, 16, depth=2, duplex=duplex)
+    if not duplex:
+        p0 = {k: v.pin_memory() for k, v in batches[0].items()}
+        o0 = (torch.empty(6, 32, 32, 16).pin_memory(), torch.empty(6, 32, 32).pin_memory(), torch.empty(6, 32, 32).pin_memory())
+        ms = sr.calibrate(p0['feat'], p0['dens'], p0['R'], p0['T'], p0['K'], p0['view2vol'], *o0, steps=4)
+        assert set(ms) == {"duplex", "half_duplex"} and all(v > 0 for v in ms.values())
+        sr.duplex = False
     outs = []
     for b in batches:
         pin = {k: v.pin_memory() for k, v in b.items()}
