@@ -397,7 +397,10 @@ def run_forge(args, rank, world, local_rank):
         sr = StreamedRenderer(model, V, N, D, depth=3, device=dev)
         # untimed: full-duplex copies (own download stream) or half-duplex (downloads queued behind the next upload) -- which one is
         # faster depends on the box's host link (one GPU: duplex; 8 GPUs behind one NUMA node: half duplex), so it is measured
-        e2e_modes = sr.calibrate(h_feat, h_dens, h_R, h_T, h_K, h_v2v, h_out, h_sil, h_dep, steps=24)
+        e2e_modes = sr.calibrate(h_feat, h_dens, h_R, h_T, h_K, h_v2v, h_out, h_sil, h_dep, steps=24, sync=barrier)
+        cal = reduce_max([e2e_modes["duplex"], e2e_modes["half_duplex"]], world, dev)     # every rank takes the same, box-wide choice
+        e2e_modes = {"duplex": cal[0], "half_duplex": cal[1]}
+        sr.duplex = cal[0] <= cal[1]
         e2e_mode = "duplex" if sr.duplex else "half_duplex"
         for _ in range(4):
             sr.submit(h_feat, h_dens, h_R, h_T, h_K, h_v2v, h_out, h_sil, h_dep)
@@ -450,7 +453,7 @@ def run_forge(args, rank, world, local_rank):
                 "api": "forge_b200.pipeline.StreamedRenderer: pinned host volumes+cameras -> H2D -> camera prep + pack + raymarch "
                        "-> D2H into pinned host images, every step; 3 batches in flight, kernels overlapped with the copies",
                 "copy_mode": e2e_mode, "copy_mode_calibration_ms_per_step": e2e_modes,
-                "copy_mode_note": "chosen by StreamedRenderer.calibrate() before the timed region (rank 0's choice shown): duplex = "
+                "copy_mode_note": "chosen by StreamedRenderer.calibrate() before the timed region (all ranks measure together, max over ranks): duplex = "
                                   "downloads on their own stream, half_duplex = downloads queued behind the next batch's upload",
                 "unpipelined_value": world * rays * e2e_steps / (e2e_serial_ms * 1e-3),
                 "unpipelined_api": "VolRender.render_features, one step at a time on one stream",

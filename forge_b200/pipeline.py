@@ -109,8 +109,11 @@ class StreamedRenderer:
             outs[2].copy_(s.depth, non_blocking=True)
             s.copied_out.record(stream)
 
-    def calibrate(self, feat, dens, R, T, K, view2vol, out_feat, out_sil, out_depth, steps=24):
-        """Run ``steps`` batches in each copy mode and keep the faster one (host links differ: see __init__).  -> dict of ms."""
+    def calibrate(self, feat, dens, R, T, K, view2vol, out_feat, out_sil, out_depth, steps=24, sync=None):
+        """Run ``steps`` batches in each copy mode and keep the faster one (host links differ: see __init__).  -> dict of ms.
+        ``sync`` (optional callable, e.g. a torch.distributed barrier) is called before each measurement so that all the ranks of
+        a box measure under the contention they will run under; a multi-rank caller may then override ``self.duplex`` with a
+        choice made on the reduced timings."""
         ms = {}
         for mode in (True, False):
             self.drain()
@@ -118,6 +121,8 @@ class StreamedRenderer:
             for _ in range(3):
                 self.submit(feat, dens, R, T, K, view2vol, out_feat, out_sil, out_depth)
             self.drain()
+            if sync is not None:
+                sync()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(self.dev)
             e0.record(self.s_in)
