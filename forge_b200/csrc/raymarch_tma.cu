@@ -48,7 +48,7 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
                         float* __restrict__ out_feat, float* __restrict__ out_sil, float* __restrict__ out_depth, int D,
                         int H, int W, int Sh, int Sw, int P, int tiles_x, int interleave) {
     constexpr int kConsWarps = 4 * kWarpsY, kTmaThreads = 32 * (kConsWarps + 1), kTH = 4 * kWarpsY;
-    constexpr bool kTuned = kMode >= 1;          // 0: first round-2 sample loop, 1: tuned instruction stream
+    constexpr bool kTuned = kMode >= 1;          // 0: first round-2 sample loop, 1 / 3 / 4: tuned instruction stream with 4 / 8 / 16 LDS.128 in flight
     // (A sample-pair mapping -- lane c takes sample k + c and reads all 8 corners, so the footprint / density / weight work is done
     // once per ray-sample instead of once per lane -- was built and measured in commit "K1-T sample-pair mapping": same instruction
     // count, 20 more live registers under the 96-register cap of 2 x 9 warps, 51 M local-memory sectors of spill traffic through L1:
@@ -247,7 +247,41 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
                 const bool inbox = (static_cast<unsigned>(xb) + 1u < static_cast<unsigned>(h.ex)) &&
                                    (static_cast<unsigned>(yb) + 1u < static_cast<unsigned>(h.ey)) &&
                                    (static_cast<unsigned>(zb) + 1u < static_cast<unsigned>(h.ez));
-                if (inbox && kTuned) {
+                if (inbox && kMode == 3) {
+                    // one z-plane at a time: its 8 LDS.128 (two corner rows) in flight before the 16 FFMA2
+                    const uint32_t a0 = brick + static_cast<uint32_t>(((zb * h.ey + yb) * h.ex + xb + c) << 6);
+                    const uint32_t sy = static_cast<uint32_t>(h.ex) << 6, sz = static_cast<uint32_t>(h.ex * h.ey) << 6;
+#pragma unroll
+                    for (int dz = 0; dz < 2; ++dz) {
+                        const uint32_t ap = a0 + (dz ? sz : 0u);
+                        float4 v[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            v[e] = lds128(ap + choff[e]);
+                            v[4 + e] = lds128(ap + sy + choff[e]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            fma4(acc + 4 * e, cw[2 * dz], v[e]);
+                            fma4(acc + 4 * e, cw[2 * dz + 1], v[4 + e]);
+                        }
+                    }
+                } else if (inbox && kMode == 4) {
+                    // all 16 LDS.128 of the sample in flight before the 32 FFMA2
+                    const uint32_t a0 = brick + static_cast<uint32_t>(((zb * h.ey + yb) * h.ex + xb + c) << 6);
+                    const uint32_t sy = static_cast<uint32_t>(h.ex) << 6, sz = static_cast<uint32_t>(h.ex * h.ey) << 6;
+                    float4 v[16];
+#pragma unroll
+                    for (int cn = 0; cn < 4; ++cn) {
+                        const uint32_t ap = a0 + ((cn & 2) ? sz : 0u) + ((cn & 1) ? sy : 0u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[4 * cn + e] = lds128(ap + choff[e]);
+                    }
+#pragma unroll
+                    for (int cn = 0; cn < 4; ++cn)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) fma4(acc + 4 * e, cw[cn], v[4 * cn + e]);
+                } else if (inbox && kTuned) {
                     // one (dz, dy) corner row at a time: its 4 LDS.128 are issued back to back, then the 8 FFMA2 (the compiler's own
                     // schedule kept 2 loads in flight per lane)
                     const uint32_t a0 = brick + static_cast<uint32_t>(((zb * h.ey + yb) * h.ex + xb + c) << 6);
@@ -331,7 +365,7 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
                             int V, int D, int H, int W, int S_h, int S_w, int P, cudaStream_t st) {
     static const int ring = [] {                // tuning knob (development): ring shape "stages x voxels per stage"
         const char* e = getenv("FORGE_K1T_RING");
-        return e ? atoi(e) : 10;
+        return e ? atoi(e) : 13;
     }();
     if (ring == 7)          // one lane per ray (raymarch_tma1.cu)
         return raymarch_fwd_tma1_launch(fn, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D, H, W, S_h,
@@ -361,6 +395,12 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
     if (ring == 10)         // tuned instruction stream (A/B against the default)
         return tma_launch_cfg<2, 880, 2, true, 1>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V,
                                                      D, H, W, S_h, S_w, P, st);
+    if (ring == 13)         // tuned loop with 16 LDS.128 in flight per lane (A/B)
+        return tma_launch_cfg<2, 880, 2, true, 4>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V,
+                                                  D, H, W, S_h, S_w, P, st);
+    if (ring == 12)         // tuned loop with 8 LDS.128 in flight per lane (A/B)
+        return tma_launch_cfg<2, 880, 2, true, 3>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V,
+                                                  D, H, W, S_h, S_w, P, st);
     if (ring == 3) FORGE_K1T(3, 552, 2);
     if (ring == 5) FORGE_K1T(2, 1700, 4);         // 16 x 16 pixel tile, one CTA per SM, twice the slab length
     if (ring == 6) FORGE_K1T(3, 1130, 4);
@@ -368,10 +408,11 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
     if (ring == 2) FORGE_K1T(2, 880, 2);          // round-2 first default (untuned instruction stream)
 #undef FORGE_K1T
     // default: the largest stages two CTAs per SM can hold (0.347 vs 0.349 ms at cfg-2, 4.68 vs 4.73 ms at cfg-4) with the tuned
-    // sample loop (folded un-normalisation, F2I + I2FP floor, 32-bit quad index, two samples per trip, 4 LDS.128 in flight):
-    // 0.348 -> 0.332 ms at cfg-2, 4.68 -> 4.49 ms at cfg-4
-    return tma_launch_cfg<2, 880, 2, true, 1>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D,
-                                                 H, W, S_h, S_w, P, st);
+    // sample loop (folded un-normalisation, F2I + I2FP floor, 32-bit quad index, two samples per trip) and all 16 LDS.128 of a
+    // sample in flight before their 32 FFMA2: 0.348 -> 0.322 ms at cfg-2, 4.68 -> 4.37 ms at cfg-4 (4 / 8 / 16 loads in flight:
+    // 0.332 / 0.328 / 0.322 ms; FORGE_K1T_RING = 10 / 12 / 13)
+    return tma_launch_cfg<2, 880, 2, true, 4>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D,
+                                              H, W, S_h, S_w, P, st);
 }
 
 }  // namespace forge
