@@ -48,7 +48,7 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
                         float* __restrict__ out_feat, float* __restrict__ out_sil, float* __restrict__ out_depth, int D,
                         int H, int W, int Sh, int Sw, int P, int tiles_x, int interleave) {
     constexpr int kConsWarps = 4 * kWarpsY, kTmaThreads = 32 * (kConsWarps + 1), kTH = 4 * kWarpsY;
-    constexpr bool kTuned = kMode >= 1;          // 0: first round-2 sample loop, 1 / 3 / 4: tuned instruction stream with 4 / 8 / 16 LDS.128 in flight
+    constexpr bool kTuned = kMode >= 1;          // 0: first round-2 sample loop, 1 / 3 / 4: tuned instruction stream with 4 / 8 / 16 LDS.128 in flight, 5: 16 in flight and one sample per loop trip (default)
     // (A sample-pair mapping -- lane c takes sample k + c and reads all 8 corners, so the footprint / density / weight work is done
     // once per ray-sample instead of once per lane -- was built and measured in commit "K1-T sample-pair mapping": same instruction
     // count, 20 more live registers under the 96-register cap of 2 x 9 warps, 51 M local-memory sectors of spill traffic through L1:
@@ -217,8 +217,10 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
         const SlabHeader h = sm.hdr[s & 7];
         const uint32_t brick = stage0 + static_cast<uint32_t>(st) * (kStageVox * 64);
         const int kend = min(h.kb, kw1);
-        // tuned: two samples per trip, so the one-ahead (footprint, quad) registers alternate instead of being copied
-#pragma unroll(kTuned ? 2 : 1)
+        // tuned (kMode 1 / 3 / 4): two samples per trip, so the one-ahead (footprint, quad) registers alternate instead of being
+        // copied; with all 16 loads of a sample in flight (kMode 5, default) one sample per trip is faster again (0.3175 vs 0.3224 ms
+        // at cfg-2, 4.344 vs 4.376 ms at cfg-4; four per trip: 0.344)
+#pragma unroll(kMode == 5 ? 1 : (kTuned ? 2 : 1))
         for (int k = max(h.ka, kw0); k < kend; ++k) {
             const float z = sm.zs[k];
             if (!kPrefetch) actn = fetch(k, fn, d4n);
@@ -266,7 +268,7 @@ raymarch_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __res
                             fma4(acc + 4 * e, cw[2 * dz + 1], v[4 + e]);
                         }
                     }
-                } else if (inbox && kMode == 4) {
+                } else if (inbox && kMode >= 4) {
                     // all 16 LDS.128 of the sample in flight before the 32 FFMA2
                     const uint32_t a0 = brick + static_cast<uint32_t>(((zb * h.ey + yb) * h.ex + xb + c) << 6);
                     const uint32_t sy = static_cast<uint32_t>(h.ex) << 6, sz = static_cast<uint32_t>(h.ex * h.ey) << 6;
@@ -365,7 +367,7 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
                             int V, int D, int H, int W, int S_h, int S_w, int P, cudaStream_t st) {
     static const int ring = [] {                // tuning knob (development): ring shape "stages x voxels per stage"
         const char* e = getenv("FORGE_K1T_RING");
-        return e ? atoi(e) : 13;
+        return e ? atoi(e) : 14;
     }();
     if (ring == 7)          // one lane per ray (raymarch_tma1.cu)
         return raymarch_fwd_tma1_launch(fn, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D, H, W, S_h,
@@ -398,6 +400,9 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
     if (ring == 13)         // tuned loop with 16 LDS.128 in flight per lane (A/B)
         return tma_launch_cfg<2, 880, 2, true, 4>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V,
                                                   D, H, W, S_h, S_w, P, st);
+    if (ring == 14)         // 16 in flight, one sample per trip (A/B)
+        return tma_launch_cfg<2, 880, 2, true, 5>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V,
+                                                  D, H, W, S_h, S_w, P, st);
     if (ring == 12)         // tuned loop with 8 LDS.128 in flight per lane (A/B)
         return tma_launch_cfg<2, 880, 2, true, 3>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V,
                                                   D, H, W, S_h, S_w, P, st);
@@ -408,10 +413,10 @@ int raymarch_fwd_tma_launch(const char* fn, const float* feat_pad, const float4*
     if (ring == 2) FORGE_K1T(2, 880, 2);          // round-2 first default (untuned instruction stream)
 #undef FORGE_K1T
     // default: the largest stages two CTAs per SM can hold (0.347 vs 0.349 ms at cfg-2, 4.68 vs 4.73 ms at cfg-4) with the tuned
-    // sample loop (folded un-normalisation, F2I + I2FP floor, 32-bit quad index, two samples per trip) and all 16 LDS.128 of a
-    // sample in flight before their 32 FFMA2: 0.348 -> 0.322 ms at cfg-2, 4.68 -> 4.37 ms at cfg-4 (4 / 8 / 16 loads in flight:
-    // 0.332 / 0.328 / 0.322 ms; FORGE_K1T_RING = 10 / 12 / 13)
-    return tma_launch_cfg<2, 880, 2, true, 4>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D,
+    // sample loop (folded un-normalisation, F2I + I2FP floor, 32-bit quad index) and all 16 LDS.128 of a sample in flight before
+    // their 32 FFMA2, one sample per trip: 0.348 -> 0.318 ms at cfg-2, 4.68 -> 4.34 ms at cfg-4 (4 / 8 / 16 loads in flight with
+    // two samples per trip: 0.332 / 0.328 / 0.322 ms; FORGE_K1T_RING = 10 / 12 / 13, default 14)
+    return tma_launch_cfg<2, 880, 2, true, 5>(fn, maps, feat_pad, dens_quad, view2vol, cam12, zs, out_feat, out_sil, out_depth, N, V, D,
                                               H, W, S_h, S_w, P, st);
 }
 
